@@ -1,0 +1,380 @@
+#include "comm_context.h"
+
+#include <algorithm>
+
+#include "kernels_direct.cuh"
+#include "kernels_tree.cuh"
+
+namespace adapcc {
+
+namespace {
+constexpr size_t kPadBytes = 16384;                       // barrier pad region
+constexpr size_t kFlagOffset = kPadBytes;                 // chunk flags follow
+constexpr size_t kSigBytes = 65536;
+constexpr size_t kStateEpoch = 0, kStateTicket = 1024, kStateErr = 1028, kStateSeq = 1032,
+                 kStateBytes = 4096;
+static_assert(kMaxBlocks * kMaxRanks * 4 <= kPadBytes, "pad too small");
+static_assert(2 * kMaxBlocks * 8 + kFlagOffset <= kSigBytes, "flag region too small");
+
+int epp_of(int wire) { return wire == F32 ? 4 : 8; }
+
+bool combo_ok(int dtype, int wire) {
+  return (dtype == F32 && (wire == F32 || wire == BF16 || wire == F16)) ||
+         (dtype == BF16 && wire == BF16) || (dtype == F16 && wire == F16);
+}
+
+// dispatch helpers --------------------------------------------------------------------
+#define ADAPCC_DISPATCH_TYPES(dtype, wire, ...)                                            \
+  [&]() -> int {                                                                           \
+    if (dtype == F32 && wire == F32) { using U = float; using W = float; __VA_ARGS__ }     \
+    if (dtype == F32 && wire == BF16) { using U = float; using W = __nv_bfloat16; __VA_ARGS__ } \
+    if (dtype == F32 && wire == F16) { using U = float; using W = __half; __VA_ARGS__ }    \
+    if (dtype == BF16 && wire == BF16) { using U = __nv_bfloat16; using W = __nv_bfloat16; __VA_ARGS__ } \
+    if (dtype == F16 && wire == F16) { using U = __half; using W = __half; __VA_ARGS__ }   \
+    set_error("unsupported dtype/wire combination %d/%d", dtype, wire);                    \
+    return -1;                                                                             \
+  }()
+
+template <typename U, typename W, int OP>
+int launch_direct(int algo, int blocks, cudaStream_t s, const DevComm& dc, const void* in, void* out,
+                  long long n, float scale, int flags, int root) {
+  const U* i = static_cast<const U*>(in);
+  U* o = static_cast<U*>(out);
+  switch (algo) {
+    case ONE_SHOT:
+      allreduce_direct_kernel<U, W, OP, ONE_SHOT><<<blocks, kThreads, 0, s>>>(dc, i, o, n, scale, flags, root);
+      break;
+    case TWO_SHOT:
+      allreduce_direct_kernel<U, W, OP, TWO_SHOT><<<blocks, kThreads, 0, s>>>(dc, i, o, n, scale, flags, root);
+      break;
+    case NVLS:
+      allreduce_direct_kernel<U, W, OP, NVLS><<<blocks, kThreads, 0, s>>>(dc, i, o, n, scale, flags, root);
+      break;
+    default:
+      set_error("launch_direct: bad algo %d", algo);
+      return -1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+CommContext::~CommContext() { destroy(); }
+
+int CommContext::init(const std::string& name, int rank, int world, int device, size_t staging_bytes,
+                      size_t heap_bytes) {
+  rank_ = rank;
+  world_ = world;
+  device_ = device;
+  if (symm_.init(name, rank, world, device)) return -1;
+  if (symm_.alloc(kSigBytes, false, &sig_)) return -1;
+  if (staging_bytes < (1u << 20)) staging_bytes = 1u << 20;
+  if (symm_.alloc(staging_bytes, true, &staging_)) return -1;
+  if (heap_bytes) {
+    if (symm_.alloc(heap_bytes, true, &heap_)) return -1;
+  }
+  CUDA_TRY(cudaMalloc(&d_state_, kStateBytes));
+  CUDA_TRY(cudaMemset(d_state_, 0, kStateBytes));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const char* e = getenv("ADAPCC_MAX_BLOCKS");
+  if (e && atoi(e) > 0) tun.max_blocks = std::min(atoi(e), kMaxBlocks);
+  e = getenv("ADAPCC_TIMEOUT_MS");
+  if (e) tun.timeout_ms = atoll(e);
+  if (world > 1 && symm_.boot().barrier()) return -1;
+  inited_ = true;
+  return 0;
+}
+
+void CommContext::destroy() {
+  if (!inited_) return;
+  inited_ = false;
+  cudaSetDevice(device_);
+  cudaDeviceSynchronize();
+  symm_.free(&heap_);
+  symm_.free(&staging_);
+  symm_.free(&sig_);
+  if (d_state_) cudaFree(d_state_);
+  d_state_ = nullptr;
+  symm_.destroy();
+}
+
+int CommContext::load_strategy_text(const std::string& xml) { return strategy_.load(xml, world_) ? 0 : -1; }
+int CommContext::load_strategy_file(const std::string& path) {
+  return strategy_.load_file(path, world_) ? 0 : -1;
+}
+
+CommContext::Window CommContext::resolve(const void* in, const void* out, size_t bytes, bool same_dtype) {
+  Window w{};
+  const char* hb = heap_.size ? (const char*)heap_.peers[rank_] : nullptr;
+  const char* p = (const char*)in;
+  if (hb && same_dtype && in == out && p >= hb && p + bytes <= hb + heap_.size &&
+      ((p - hb) & 15) == 0) {
+    const size_t off = (size_t)(p - hb);
+    for (int r = 0; r < world_; ++r) w.data[r] = (char*)heap_.peers[r] + off;
+    w.mc = heap_.mc ? (char*)heap_.mc + off : nullptr;
+    w.capacity = heap_.size - off;
+    w.zero_copy = true;
+    return w;
+  }
+  for (int r = 0; r < world_; ++r) w.data[r] = (char*)staging_.peers[r];
+  w.mc = (char*)staging_.mc;
+  w.capacity = staging_.size;
+  w.zero_copy = false;
+  return w;
+}
+
+int CommContext::fill_comm(const std::vector<int>& parts, const Window& w, void* out) {
+  DevComm& dc = *static_cast<DevComm*>(out);
+  memset(&dc, 0, sizeof(dc));
+  dc.rank = rank_;
+  dc.world = world_;
+  dc.n_active = (int)parts.size();
+  dc.my_index = -1;
+  for (int i = 0; i < (int)parts.size(); ++i) {
+    if (parts[i] < 0 || parts[i] >= world_) { set_error("active rank %d out of range", parts[i]); return -1; }
+    if (i && parts[i] <= parts[i - 1]) { set_error("active list must be sorted and unique"); return -1; }
+    dc.active_ranks[i] = parts[i];
+    if (parts[i] == rank_) dc.my_index = i;
+  }
+  for (int r = 0; r < world_; ++r) {
+    dc.data[r] = w.data[r];
+    dc.pad[r] = (uint32_t*)sig_.peers[r];
+    dc.flag[r] = (unsigned long long*)((char*)sig_.peers[r] + kFlagOffset);
+  }
+  dc.mc_data = w.mc;
+  dc.bar_epoch = (uint32_t*)(d_state_ + kStateEpoch);
+  dc.ticket = (uint32_t*)(d_state_ + kStateTicket);
+  dc.err = (uint32_t*)(d_state_ + kStateErr);
+  dc.seq = (unsigned long long*)(d_state_ + kStateSeq);
+  dc.timeout_ns = tun.timeout_ms > 0 ? (unsigned long long)tun.timeout_ms * 1000000ull : 0ull;
+  return 0;
+}
+
+int CommContext::pick_algo(int algo, long long wire_bytes, int op, int wire, bool all_active,
+                           const Window& w) {
+  const bool nvls_ok = w.mc != nullptr && all_active && !(op == MAX && wire == F32);
+  if (algo == NVLS && !nvls_ok) {
+    set_error("NVLS requested but unavailable (multicast=%d all_active=%d op=%d)", (int)(w.mc != nullptr),
+              (int)all_active, op);
+    return -1;
+  }
+  if (algo == ONE_SHOT || algo == TWO_SHOT || algo == NVLS) return algo;
+  if (algo != AUTO) { set_error("bad algo %d", algo); return -1; }
+  if (wire_bytes <= tun.one_shot_max_bytes) return ONE_SHOT;
+  if (nvls_ok && wire_bytes >= tun.nvls_min_bytes) return NVLS;
+  return TWO_SHOT;
+}
+
+int CommContext::skip_op(cudaStream_t stream) {
+  DevComm dc;
+  Window w = resolve(nullptr, nullptr, 0, false);
+  if (fill_comm({}, w, &dc)) return -1;
+  skip_op_kernel<<<1, 32, 0, stream>>>(dc);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int CommContext::reduce(const void* in, void* out, long long count, int dtype, int wire, int op, int algo,
+                        int root, const std::vector<int>& active, cudaStream_t stream) {
+  if (!inited_) { set_error("context not initialised"); return -1; }
+  if (!combo_ok(dtype, wire)) { set_error("unsupported dtype/wire %d/%d", dtype, wire); return -1; }
+  if (count < 0) { set_error("negative count"); return -1; }
+  const bool mine = std::find(active.begin(), active.end(), rank_) != active.end();
+  if (!mine || count == 0) return skip_op(stream);
+  const int na = (int)active.size();
+  int root_index = -1;
+  int flags = 0;
+  if (root >= 0) {
+    for (int i = 0; i < na; ++i)
+      if (active[i] == root) root_index = i;
+    if (root_index < 0) { set_error("reduce root %d is not in the active list", root); return -1; }
+    flags |= F_ROOT_ONLY;
+  }
+  const size_t esize = dtype_size(dtype), wsize = dtype_size(wire);
+  if (na == 1) {
+    if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, (size_t)count * esize, cudaMemcpyDeviceToDevice, stream));
+    return skip_op(stream);
+  }
+  const float scale = (op == AVG) ? 1.f / (float)na : 1.f;
+  const int kop = (op == MAX) ? MAX : SUM;
+  Window w = resolve(in, out, (size_t)count * esize, dtype == wire);
+  int a = pick_algo(algo, count * (long long)wsize, kop, wire, na == world_, w);
+  if (a < 0) return -1;
+  if (a == ONE_SHOT && w.zero_copy) {      // in-place one-shot would race with peers' reads
+    w = Window{};
+    for (int r = 0; r < world_; ++r) w.data[r] = (char*)staging_.peers[r];
+    w.mc = (char*)staging_.mc;
+    w.capacity = staging_.size;
+    w.zero_copy = false;
+  }
+  last_algo = a;
+  if (w.zero_copy) flags |= F_ZERO_COPY;
+  const int epp = epp_of(wire);
+  // staged ops larger than the window run as back-to-back pieces
+  const long long cap_elems = w.zero_copy ? count : (long long)(w.capacity / 16) * epp;
+  DevComm dc;
+  if (fill_comm(active, w, &dc)) return -1;
+  long long done = 0;
+  while (done < count) {
+    const long long n = std::min(count - done, cap_elems);
+    const long long npacks = (n + epp - 1) / epp;
+    int blocks = (int)std::min<long long>((npacks + (long long)kThreads * kUnroll - 1) / ((long long)kThreads * kUnroll),
+                                          (long long)std::min(tun.max_blocks, kMaxBlocks));
+    if (blocks < 1) blocks = 1;
+    const char* pin = (const char*)in + (size_t)done * esize;
+    char* pout = (char*)out + (size_t)done * esize;
+    if (w.zero_copy && done) { set_error("internal: zero-copy op split into pieces"); return -1; }
+    int rc = ADAPCC_DISPATCH_TYPES(dtype, wire, {
+      if (kop == MAX) return launch_direct<U, W, MAX>(a, blocks, stream, dc, pin, pout, n, scale, flags, root_index);
+      return launch_direct<U, W, SUM>(a, blocks, stream, dc, pin, pout, n, scale, flags, root_index);
+    });
+    if (rc) return rc;
+    done += n;
+  }
+  return 0;
+}
+
+int CommContext::allreduce(const void* in, void* out, long long count, int dtype, int wire, int op, int algo,
+                           const std::vector<int>& active, cudaStream_t stream) {
+  return reduce(in, out, count, dtype, wire, op, algo, -1, active, stream);
+}
+
+int CommContext::broadcast(void* buf, long long count, int dtype, int root, const std::vector<int>& active,
+                           cudaStream_t stream) {
+  if (!inited_) { set_error("context not initialised"); return -1; }
+  const bool mine = std::find(active.begin(), active.end(), rank_) != active.end();
+  if (!mine || count == 0) return skip_op(stream);
+  const int na = (int)active.size();
+  int root_index = -1;
+  for (int i = 0; i < na; ++i)
+    if (active[i] == root) root_index = i;
+  if (root_index < 0) { set_error("broadcast root %d is not in the active list", root); return -1; }
+  if (na == 1) return skip_op(stream);
+  const size_t esize = dtype_size(dtype);
+  Window w = resolve(buf, buf, (size_t)count * esize, true);
+  const int wire = dtype;
+  const int epp = epp_of(wire);
+  const long long cap_elems = w.zero_copy ? count : (long long)(w.capacity / 16) * epp;
+  const int use_mc = (w.mc != nullptr && na == world_) ? 1 : 0;
+  DevComm dc;
+  if (fill_comm(active, w, &dc)) return -1;
+  long long done = 0;
+  while (done < count) {
+    const long long n = std::min(count - done, cap_elems);
+    const long long npacks = (n + epp - 1) / epp;
+    int blocks = (int)std::min<long long>((npacks + (long long)kThreads * kUnroll - 1) / ((long long)kThreads * kUnroll),
+                                          (long long)std::min(tun.max_blocks, kMaxBlocks));
+    if (blocks < 1) blocks = 1;
+    char* p = (char*)buf + (size_t)done * esize;
+    const int flags = w.zero_copy ? F_ZERO_COPY : 0;
+    int rc = ADAPCC_DISPATCH_TYPES(dtype, wire, {
+      broadcast_direct_kernel<U, W><<<blocks, kThreads, 0, stream>>>(dc, (U*)p, n, root_index, use_mc, flags);
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    });
+    if (rc) return rc;
+    done += n;
+  }
+  return 0;
+}
+
+int CommContext::tree_collective(int prim, const void* in, void* out, long long count, int dtype, int wire,
+                                 int op, long long chunk_bytes, const std::vector<int>& active,
+                                 cudaStream_t stream) {
+  if (!inited_) { set_error("context not initialised"); return -1; }
+  if (strategy_.trees.empty()) { set_error("tree collective without a loaded strategy"); return -1; }
+  if (!combo_ok(dtype, wire)) { set_error("unsupported dtype/wire %d/%d", dtype, wire); return -1; }
+  if (prim != ALLREDUCE && prim != REDUCE && prim != BOARDCAST) { set_error("bad tree primitive %d", prim); return -1; }
+  std::vector<bool> act(world_, false);
+  for (int r : active) {
+    if (r < 0 || r >= world_) { set_error("active rank %d out of range", r); return -1; }
+    act[r] = true;
+  }
+  const int nt = (int)strategy_.trees.size();
+  // roles of every rank (participants must agree everywhere), then mine
+  std::vector<int> participants;
+  std::vector<HostTreeRole> mine(nt);
+  for (int r = 0; r < world_; ++r) {
+    bool any = false;
+    for (int t = 0; t < nt; ++t) {
+      HostTreeRole role = tree_role(strategy_.trees[t], r, act, prim, tun.relay_mode);
+      any |= role.any();
+      if (r == rank_) mine[t] = role;
+    }
+    if (any) participants.push_back(r);
+  }
+  const bool me_in = std::find(participants.begin(), participants.end(), rank_) != participants.end();
+  if (!me_in || count == 0) return skip_op(stream);
+
+  const size_t esize = dtype_size(dtype);
+  const int epp = epp_of(wire);
+  int n_contrib = 0;
+  for (int r : active) (void)r, ++n_contrib;
+  const float scale = (op == AVG && n_contrib > 0) ? 1.f / (float)n_contrib : 1.f;
+  const int kop = (op == MAX) ? MAX : SUM;
+
+  Window w{};
+  for (int r = 0; r < world_; ++r) w.data[r] = (char*)staging_.peers[r];
+  w.mc = (char*)staging_.mc;
+  w.capacity = staging_.size;
+  w.zero_copy = false;
+  DevComm dc;
+  if (fill_comm(participants, w, &dc)) return -1;
+
+  TreePlan plan;
+  memset(&plan, 0, sizeof(plan));
+  plan.n_trees = nt;
+  plan.do_reduce = prim != BOARDCAST;
+  plan.do_bcast = prim != REDUCE;
+  if (chunk_bytes < 16) chunk_bytes = 16;
+  plan.chunk_packs = chunk_bytes / 16;
+  for (int t = 0; t < nt; ++t) {
+    TreeRole& tr = plan.role[t];
+    tr.parent = mine[t].parent;
+    tr.flags = mine[t].flags;
+    tr.n_children = (int)mine[t].children.size();
+    if (tr.n_children > kMaxChildren) { set_error("too many children in tree %d", t); return -1; }
+    for (int i = 0; i < tr.n_children; ++i) tr.children[i] = mine[t].children[i];
+  }
+  const long long cap_elems = (long long)(w.capacity / 16) * epp;
+  long long done = 0;
+  while (done < count) {
+    const long long n = std::min(count - done, cap_elems);
+    const long long npacks = (n + epp - 1) / epp;
+    const long long per = (npacks + nt - 1) / nt;
+    long long max_chunks = 0;
+    for (int t = 0; t <= nt; ++t) plan.slice_begin[t] = std::min<long long>((long long)t * per, npacks);
+    max_chunks = (per + plan.chunk_packs - 1) / plan.chunk_packs;
+    const long long items = max_chunks * nt;
+    int blocks = (int)std::min<long long>(items, (long long)std::min(tun.tree_blocks, kMaxBlocks));
+    if (blocks < 1) blocks = 1;
+    const char* pin = (const char*)in + (size_t)done * esize;
+    char* pout = (char*)out + (size_t)done * esize;
+    int rc = ADAPCC_DISPATCH_TYPES(dtype, wire, {
+      if (kop == MAX)
+        tree_collective_kernel<U, W, MAX><<<blocks, kThreads, 0, stream>>>(dc, plan, (const U*)pin, (U*)pout, n, scale);
+      else
+        tree_collective_kernel<U, W, SUM><<<blocks, kThreads, 0, stream>>>(dc, plan, (const U*)pin, (U*)pout, n, scale);
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    });
+    if (rc) return rc;
+    done += n;
+  }
+  return 0;
+}
+
+int CommContext::check(cudaStream_t stream) {
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  uint32_t err = 0;
+  CUDA_TRY(cudaMemcpy(&err, d_state_ + kStateErr, sizeof(err), cudaMemcpyDeviceToHost));
+  if (err) {
+    CUDA_TRY(cudaMemset(d_state_ + kStateErr, 0, sizeof(err)));
+    set_error("device-side wait timed out (code %u): a peer did not arrive within %lld ms", err,
+              tun.timeout_ms);
+    return (int)err;
+  }
+  return 0;
+}
+
+}  // namespace adapcc

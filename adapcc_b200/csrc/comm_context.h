@@ -1,0 +1,83 @@
+// Host-side communicator context: symmetric windows, signal pads, device-resident op
+// state, strategy, and the launchers for every collective kernel.
+//
+// One context == one "transmission context" of the reference
+// (allreduceContext/reduceContext/boardcastContext, /root/reference/csrc/include/trans.h:219-255)
+// but without threads or queues: a collective is one kernel launch on the caller's stream.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "schedule.h"
+#include "symm_mem.h"
+
+namespace adapcc {
+
+struct Tunables {
+  int max_blocks = 64;                 // CTAs per collective kernel (same on all ranks)
+  long long one_shot_max_bytes = 256 << 10;   // wire bytes: <= -> one-shot
+  long long nvls_min_bytes = 0;        // wire bytes: >= -> NVLS when available
+  int relay_mode = RELAY_FORWARD;
+  long long timeout_ms = 30000;
+  int tree_blocks = 64;
+};
+
+class CommContext {
+ public:
+  ~CommContext();
+  int init(const std::string& name, int rank, int world, int device, size_t staging_bytes,
+           size_t heap_bytes);
+  void destroy();
+
+  int load_strategy_text(const std::string& xml);
+  int load_strategy_file(const std::string& path);
+
+  // Direct collectives. `active`: sorted world ranks taking part (must contain rank_ to
+  // launch anything but a sequence bump). In-place allowed (in == out).
+  int allreduce(const void* in, void* out, long long count, int dtype, int wire, int op, int algo,
+                const std::vector<int>& active, cudaStream_t stream);
+  int reduce(const void* in, void* out, long long count, int dtype, int wire, int op, int algo,
+             int root, const std::vector<int>& active, cudaStream_t stream);
+  int broadcast(void* buf, long long count, int dtype, int root, const std::vector<int>& active,
+                cudaStream_t stream);
+  // Strategy-driven tree collective (prim = ALLREDUCE / REDUCE / BOARDCAST).
+  int tree_collective(int prim, const void* in, void* out, long long count, int dtype, int wire,
+                      int op, long long chunk_bytes, const std::vector<int>& active,
+                      cudaStream_t stream);
+  int skip_op(cudaStream_t stream);
+
+  // Reads (and clears) the sticky device error word; synchronises the stream.
+  int check(cudaStream_t stream);
+
+  void* heap_ptr() const { return heap_.size ? heap_.peers[rank_] : nullptr; }
+  size_t heap_bytes() const { return heap_.size; }
+  size_t staging_bytes() const { return staging_.size; }
+  bool has_multicast() const { return staging_.mc != nullptr; }
+  bool heap_multicast() const { return heap_.mc != nullptr; }
+  int symm_backend() const { return staging_.backend; }
+  int rank() const { return rank_; }
+  int world() const { return world_; }
+  const Strategy& strategy() const { return strategy_; }
+  Tunables tun;
+  int last_algo = 0;                   // algorithm picked by the last allreduce (for tests)
+  SymmContext& symm() { return symm_; }
+  void* peer_heap_ptr(int r) const { return heap_.peers[r]; }
+  void* peer_staging_ptr(int r) const { return staging_.peers[r]; }
+
+ private:
+  struct Window { char* data[kMaxRanks]; char* mc; size_t capacity; bool zero_copy; };
+  // Resolve where the op's data lives: inside the heap (zero copy) or the staging window.
+  Window resolve(const void* in, const void* out, size_t bytes_wire, bool same_dtype);
+  int fill_comm(const std::vector<int>& participants, const Window& w, void* dc_out);
+  int pick_algo(int algo, long long wire_bytes, int op, int wire, bool all_active, const Window& w);
+
+  SymmContext symm_;
+  SymmBuffer staging_, heap_, sig_;
+  char* d_state_ = nullptr;            // bar_epoch[], ticket, err, seq
+  Strategy strategy_;
+  int rank_ = 0, world_ = 1, device_ = 0;
+  bool inited_ = false;
+};
+
+}  // namespace adapcc

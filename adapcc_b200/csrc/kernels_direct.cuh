@@ -1,0 +1,272 @@
+// Direct (switch-topology) collectives on symmetric memory: one-shot, two-shot and NVLS
+// all-reduce / reduce, plus direct broadcast. These are the "uniform NVSwitch" schedules
+// the synthesizer can pick besides the reference-style trees. Every kernel fuses what the
+// reference runs as separate engine ops with host syncs in between
+// (/root/reference/csrc/allreduce.cu:568-654, /root/reference/csrc/run.cu:103-127):
+//   stage-in  : user tensor -> symmetric window, fused dtype cast (fp32 -> bf16 wire)
+//   transfer  : in-kernel peer ld/st (or multimem) over NVLink, fused reduction in fp32
+//   stage-out : symmetric window -> user tensor, fused 1/N scale + cast back
+// and a "zero-copy" mode when the tensor already lives in the symmetric heap.
+#pragma once
+#include "device_prims.cuh"
+
+namespace adapcc {
+
+constexpr int kThreads = 512;
+constexpr int kUnroll = 4;
+
+enum DirectFlags : int {
+  F_ZERO_COPY = 1,   // tensor is inside the symmetric window (data[] already point at it)
+  F_ROOT_ONLY = 2,   // reduce-to-root: only active index `root` receives the result
+};
+
+// Work partition: packs [0, npacks) are cut into `nslices` contiguous slices of `pps`
+// packs; inside a slice, pack j belongs to block (j / kThreads) % gridDim.x in EVERY
+// phase, so block b only ever consumes data that block b of a peer produced and a
+// per-block barrier is sufficient.
+struct Partition {
+  long long npacks, pps;
+  int nslices;
+  __device__ __forceinline__ long long slice_begin(int s) const { return (long long)s * pps; }
+  __device__ __forceinline__ long long slice_count(int s) const {
+    long long b = (long long)s * pps;
+    long long c = npacks - b;
+    return c < 0 ? 0 : (c > pps ? pps : c);
+  }
+};
+
+template <typename U, typename W>
+__device__ __forceinline__ void stage_in(const Partition& P, const U* __restrict__ in, long long n,
+                                         bool vec_ok, char* __restrict__ local) {
+  constexpr int kEpp = WireTraits<W>::kEpp;
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (int s = 0; s < P.nslices; ++s) {
+    const long long base = P.slice_begin(s), cnt = P.slice_count(s);
+    for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < cnt; j0 += stride * kUnroll) {
+      float f[kUnroll][kEpp];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const long long j = j0 + u * stride;
+        if (j < cnt) load_user<U, kEpp>(in, (base + j) * kEpp, n, vec_ok, f[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const long long j = j0 + u * stride;
+        if (j < cnt) st16(local + (base + j) * 16, pack<W>(f[u]));
+      }
+    }
+  }
+}
+
+template <typename U, typename W>
+__device__ __forceinline__ void stage_out(const Partition& P, U* __restrict__ out, long long n,
+                                          bool vec_ok, const char* __restrict__ local, float scale) {
+  constexpr int kEpp = WireTraits<W>::kEpp;
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (int s = 0; s < P.nslices; ++s) {
+    const long long base = P.slice_begin(s), cnt = P.slice_count(s);
+    for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < cnt; j0 += stride * kUnroll) {
+      uint4 v[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const long long j = j0 + u * stride;
+        if (j < cnt) v[u] = ld16(local + (base + j) * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const long long j = j0 + u * stride;
+        if (j < cnt) {
+          float f[kEpp];
+          unpack<W>(v[u], f);
+#pragma unroll
+          for (int i = 0; i < kEpp; ++i) f[i] *= scale;
+          store_user<U, kEpp>(out, (base + j) * kEpp, n, vec_ok, f);
+        }
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// all-reduce / reduce, direct algorithms
+// ----------------------------------------------------------------------------------
+template <typename U, typename W, int OP, int ALGO>
+__global__ void __launch_bounds__(kThreads, 1)
+allreduce_direct_kernel(const __grid_constant__ DevComm c, const U* __restrict__ in, U* __restrict__ out,
+                        long long n, float scale, int flags, int root) {
+  constexpr int kEpp = WireTraits<W>::kEpp;
+  uint32_t epoch = c.bar_epoch[blockIdx.x];
+  const int na = c.n_active, me = c.my_index;
+  const bool zero_copy = flags & F_ZERO_COPY;
+  const bool root_only = flags & F_ROOT_ONLY;
+  const bool in_vec = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  const bool out_vec = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  char* const local = c.data[c.rank];
+
+  Partition P;
+  P.npacks = (n + kEpp - 1) / kEpp;
+  P.nslices = (ALGO == ONE_SHOT) ? 1 : na;
+  P.pps = (P.npacks + P.nslices - 1) / P.nslices;
+  const long long stride = (long long)gridDim.x * kThreads;
+
+  // ---- phase 0: publish my contribution -------------------------------------------
+  if (!zero_copy) stage_in<U, W>(P, in, n, in_vec, local);
+  block_barrier(c, epoch);
+
+  // ---- phase 1: reduce (+ redistribute) -------------------------------------------
+  if (ALGO == ONE_SHOT) {
+    // every rank pulls every peer's window and reduces locally, fixed rank order so all
+    // replicas get bit-identical sums. Result goes straight to the user tensor.
+    if (!root_only || me == root) {
+      for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < P.npacks; j0 += stride) {
+        uint4 v[kMaxRanks];
+#pragma unroll
+        for (int a = 0; a < kMaxRanks; ++a)
+          if (a < na) v[a] = ld16(c.data[c.active_ranks[a]] + j0 * 16);
+        float acc[kEpp];
+#pragma unroll
+        for (int i = 0; i < kEpp; ++i) acc[i] = red_identity<OP>();
+#pragma unroll
+        for (int a = 0; a < kMaxRanks; ++a)
+          if (a < na) {
+            float f[kEpp];
+            unpack<W>(v[a], f);
+#pragma unroll
+            for (int i = 0; i < kEpp; ++i) acc[i] = red_apply<OP>(acc[i], f[i]);
+          }
+#pragma unroll
+        for (int i = 0; i < kEpp; ++i) acc[i] *= scale;
+        store_user<U, kEpp>(out, j0 * kEpp, n, out_vec, acc);
+      }
+    }
+    // peers may still be reading my window: nobody leaves before everyone is done
+    block_barrier(c, epoch);
+  } else {
+    const long long base = P.slice_begin(me), cnt = P.slice_count(me);
+    if (ALGO == TWO_SHOT) {
+      for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < cnt; j0 += stride) {
+        const long long off = (base + j0) * 16;
+        uint4 v[kMaxRanks];
+#pragma unroll
+        for (int a = 0; a < kMaxRanks; ++a)
+          if (a < na) {
+            int idx = me + a; if (idx >= na) idx -= na;       // stagger peers
+            v[a] = ld16(c.data[c.active_ranks[idx]] + off);
+          }
+        float acc[kEpp];
+#pragma unroll
+        for (int i = 0; i < kEpp; ++i) acc[i] = red_identity<OP>();
+#pragma unroll
+        for (int a = 0; a < kMaxRanks; ++a)
+          if (a < na) {
+            float f[kEpp];
+            unpack<W>(v[a], f);
+#pragma unroll
+            for (int i = 0; i < kEpp; ++i) acc[i] = red_apply<OP>(acc[i], f[i]);
+          }
+        if (zero_copy) {
+#pragma unroll
+          for (int i = 0; i < kEpp; ++i) acc[i] *= scale;
+        }
+        const uint4 r = pack<W>(acc);
+        if (root_only) {
+          st16(c.data[c.active_ranks[root]] + off, r);
+        } else {
+#pragma unroll
+          for (int a = 0; a < kMaxRanks; ++a)
+            if (a < na) {
+              int idx = me + a; if (idx >= na) idx -= na;
+              st16(c.data[c.active_ranks[idx]] + off, r);
+            }
+        }
+      }
+    } else {  // NVLS: the switch reduces on the way in and replicates on the way out
+      for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < cnt; j0 += stride * kUnroll) {
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const long long j = j0 + u * stride;
+          if (j < cnt) v[u] = mc_ld_reduce<W, OP>(c.mc_data + (base + j) * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const long long j = j0 + u * stride;
+          if (j < cnt) {
+            if (zero_copy && scale != 1.f) {
+              float f[kEpp];
+              unpack<W>(v[u], f);
+#pragma unroll
+              for (int i = 0; i < kEpp; ++i) f[i] *= scale;
+              v[u] = pack<W>(f);
+            }
+            if (root_only) st16(c.data[c.active_ranks[root]] + (base + j) * 16, v[u]);
+            else mc_st16(c.mc_data + (base + j) * 16, v[u]);
+          }
+        }
+      }
+    }
+    block_barrier(c, epoch);
+    // ---- phase 2: hand the result back to the caller ------------------------------
+    if (!zero_copy && (!root_only || me == root))
+      stage_out<U, W>(P, out, n, out_vec, local, scale);
+  }
+  finish_op(c, epoch);
+}
+
+// ----------------------------------------------------------------------------------
+// broadcast, direct: root pushes (multimem.st when available, else one store per peer)
+// ----------------------------------------------------------------------------------
+template <typename U, typename W>
+__global__ void __launch_bounds__(kThreads, 1)
+broadcast_direct_kernel(const __grid_constant__ DevComm c, U* __restrict__ buf, long long n, int root,
+                        int use_mc, int flags) {
+  constexpr int kEpp = WireTraits<W>::kEpp;
+  uint32_t epoch = c.bar_epoch[blockIdx.x];
+  const int na = c.n_active, me = c.my_index;
+  const bool zero_copy = flags & F_ZERO_COPY;
+  const bool vec = (reinterpret_cast<uintptr_t>(buf) & 15) == 0;
+  Partition P;
+  P.npacks = (n + kEpp - 1) / kEpp;
+  P.nslices = 1;
+  P.pps = P.npacks;
+  const long long stride = (long long)gridDim.x * kThreads;
+
+  // everyone must have entered the op before the root overwrites their window
+  block_barrier(c, epoch);
+  if (me == root) {
+    for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < P.npacks; j0 += stride * kUnroll) {
+      uint4 v[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const long long j = j0 + u * stride;
+        if (j < P.npacks) {
+          if (zero_copy) {
+            v[u] = ld16(c.data[c.rank] + j * 16);
+          } else {
+            float f[kEpp];
+            load_user<U, kEpp>(buf, j * kEpp, n, vec, f);
+            v[u] = pack<W>(f);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const long long j = j0 + u * stride;
+        if (j < P.npacks) {
+          if (use_mc) {
+            mc_st16(c.mc_data + j * 16, v[u]);
+          } else {
+#pragma unroll
+            for (int a = 0; a < kMaxRanks; ++a)
+              if (a < na && a != me) st16(c.data[c.active_ranks[a]] + j * 16, v[u]);
+          }
+        }
+      }
+    }
+  }
+  block_barrier(c, epoch);
+  if (!zero_copy && me != root) stage_out<U, W>(P, buf, n, vec, c.data[c.rank], 1.f);
+  finish_op(c, epoch);
+}
+
+}  // namespace adapcc

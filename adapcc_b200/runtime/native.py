@@ -1,0 +1,284 @@
+"""ctypes binding of ``libadapcc.so`` (the native runtime).
+
+The reference binds ``communicator.so`` with ``ctypes.CDLL`` and passes raw ``data_ptr()``s
+(/root/reference/adapcc.py:17-24, /root/reference/commu.py:124-134). We keep that shape — one
+C ABI, no torch C++ extension in the way — but the calls are asynchronous launches on a CUDA
+stream instead of blocking thread hand-offs.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import c_char_p, c_int, c_longlong, c_ulonglong, c_void_p
+from pathlib import Path
+from typing import Optional, Sequence
+
+from ..constants import ALGO_IDS, DTYPE_IDS, OP_IDS
+
+_LIB = None
+_LIB_LOCK = threading.Lock()
+_LIB_PATH = Path(__file__).resolve().parent.parent / "_C" / "libadapcc.so"
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
+    """Load (building in-tree first if needed) the native runtime. Fails loudly."""
+    global _LIB
+    with _LIB_LOCK:
+        if _LIB is not None:
+            return _LIB
+        if not _LIB_PATH.exists():
+            if not build_if_missing:
+                raise NativeError(f"{_LIB_PATH} is missing; run `python -m adapcc_b200.build`")
+            from .. import build as _build
+
+            _build.build()
+        lib = ctypes.CDLL(str(_LIB_PATH), mode=ctypes.RTLD_GLOBAL)
+        lib.adapcc_last_error.restype = c_char_p
+        lib.adapcc_ctx_create.restype = c_void_p
+        lib.adapcc_ctx_create.argtypes = [c_char_p, c_int, c_int, c_int, c_ulonglong, c_ulonglong]
+        lib.adapcc_ctx_destroy.argtypes = [c_void_p]
+        lib.adapcc_ctx_info.argtypes = [c_void_p, ctypes.POINTER(c_int)]
+        lib.adapcc_ctx_heap_ptr.restype = c_void_p
+        lib.adapcc_ctx_heap_ptr.argtypes = [c_void_p]
+        lib.adapcc_ctx_heap_bytes.restype = c_ulonglong
+        lib.adapcc_ctx_heap_bytes.argtypes = [c_void_p]
+        lib.adapcc_ctx_staging_bytes.restype = c_ulonglong
+        lib.adapcc_ctx_staging_bytes.argtypes = [c_void_p]
+        lib.adapcc_ctx_peer_heap_ptr.restype = c_void_p
+        lib.adapcc_ctx_peer_heap_ptr.argtypes = [c_void_p, c_int]
+        lib.adapcc_ctx_peer_staging_ptr.restype = c_void_p
+        lib.adapcc_ctx_peer_staging_ptr.argtypes = [c_void_p, c_int]
+        lib.adapcc_ctx_last_algo.argtypes = [c_void_p]
+        lib.adapcc_ctx_set_tunable.argtypes = [c_void_p, c_int, c_longlong]
+        lib.adapcc_ctx_load_strategy.argtypes = [c_void_p, c_char_p]
+        lib.adapcc_ctx_load_strategy_text.argtypes = [c_void_p, c_char_p]
+        ip = ctypes.POINTER(c_int)
+        lib.adapcc_allreduce.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
+                                         c_int, ip, c_int, c_void_p]
+        lib.adapcc_reduce.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_int,
+                                      c_int, ip, c_int, c_void_p]
+        lib.adapcc_broadcast.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_int, ip, c_int, c_void_p]
+        lib.adapcc_tree_collective.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_int, c_int,
+                                               c_int, c_longlong, ip, c_int, c_void_p]
+        lib.adapcc_skip_op.argtypes = [c_void_p, c_void_p]
+        lib.adapcc_ctx_check.argtypes = [c_void_p, c_void_p]
+        lib.adapcc_ctx_host_barrier.argtypes = [c_void_p]
+        lib.adapcc_relay_control.argtypes = [c_char_p, c_int, c_int, c_int, ip, c_int, ip, c_int]
+        lib.adapcc_tree_role.argtypes = [c_char_p, c_int, c_int, c_int, ip, c_int, c_int, c_int, ip, c_int]
+        _LIB = lib
+        return lib
+
+
+def last_error() -> str:
+    lib = load_library()
+    e = lib.adapcc_last_error()
+    return e.decode("utf-8", "replace") if e else ""
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise NativeError(f"{what} failed: {last_error()}")
+
+
+def _int_array(values: Sequence[int]):
+    arr = (c_int * max(1, len(values)))(*values)
+    return arr
+
+
+TUNABLE_KEYS = {"max_blocks": 0, "one_shot_max_bytes": 1, "nvls_min_bytes": 2, "relay_mode": 3,
+                "timeout_ms": 4, "tree_blocks": 5}
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ holder so torch can view native symmetric memory."""
+
+    def __init__(self, ptr: int, nbytes: int, owner):
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None,
+        }
+        self._owner = owner
+
+
+class NativeComm:
+    """One native communicator context (symmetric windows + signal pads + kernels)."""
+
+    def __init__(self, name: str, rank: int, world: int, device: int, staging_bytes: int = 256 << 20,
+                 heap_bytes: int = 0):
+        self.lib = load_library()
+        self.rank, self.world, self.device = rank, world, device
+        h = self.lib.adapcc_ctx_create(name.encode(), rank, world, device, staging_bytes, heap_bytes)
+        if not h:
+            raise NativeError(f"adapcc_ctx_create(rank={rank}, world={world}, dev={device}) failed: {last_error()}")
+        self.handle = c_void_p(h)
+        self._heap_off = 0
+        info = (c_int * 8)()
+        self.lib.adapcc_ctx_info(self.handle, info)
+        self.symm_backend = {0: "vmm", 1: "cuda_ipc"}.get(info[0], str(info[0]))
+        self.multicast = bool(info[1])
+        self.heap_multicast = bool(info[2])
+
+    # -- lifecycle ---------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.adapcc_ctx_destroy(self.handle)
+            self.handle = c_void_p(None)
+
+    def __del__(self):  # best effort; explicit close() is collective and preferred
+        pass
+
+    # -- configuration -----------------------------------------------------------------
+    def set_tunable(self, key: str, value: int) -> None:
+        _check(self.lib.adapcc_ctx_set_tunable(self.handle, TUNABLE_KEYS[key], int(value)), f"set_tunable({key})")
+
+    def load_strategy(self, path_or_text: str) -> int:
+        if path_or_text.lstrip().startswith("<"):
+            _check(self.lib.adapcc_ctx_load_strategy_text(self.handle, path_or_text.encode()), "load_strategy_text")
+        else:
+            _check(self.lib.adapcc_ctx_load_strategy(self.handle, os.fspath(path_or_text).encode()), "load_strategy")
+        info = (c_int * 8)()
+        self.lib.adapcc_ctx_info(self.handle, info)
+        return info[5]
+
+    @property
+    def last_algo(self) -> int:
+        return self.lib.adapcc_ctx_last_algo(self.handle)
+
+    @property
+    def staging_bytes(self) -> int:
+        return int(self.lib.adapcc_ctx_staging_bytes(self.handle))
+
+    @property
+    def heap_bytes(self) -> int:
+        return int(self.lib.adapcc_ctx_heap_bytes(self.handle))
+
+    # -- symmetric heap ------------------------------------------------------------------
+    def heap_tensor(self, nbytes: Optional[int] = None, offset: int = 0):
+        """uint8 torch view of (part of) this rank's symmetric heap."""
+        import torch
+
+        base = self.lib.adapcc_ctx_heap_ptr(self.handle)
+        if not base:
+            raise NativeError("context has no symmetric heap (heap_bytes=0)")
+        total = self.heap_bytes
+        nbytes = total - offset if nbytes is None else nbytes
+        if offset + nbytes > total:
+            raise NativeError(f"heap view [{offset}, {offset + nbytes}) exceeds {total} bytes")
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(_CudaArray(base + offset, nbytes, self), device=f"cuda:{self.device}")
+
+    def symm_empty(self, numel: int, dtype):
+        """Bump-allocate a tensor inside the symmetric heap (same offset on every rank as long as
+        every rank performs the same sequence of allocations). Collectives on such tensors are
+        zero-copy: peers read/write them directly over NVLink."""
+        import torch
+
+        esize = torch.empty((), dtype=dtype).element_size()
+        nbytes = numel * esize
+        off = (self._heap_off + 255) // 256 * 256
+        t = self.heap_tensor(nbytes, off).view(dtype)
+        self._heap_off = off + nbytes
+        return t
+
+    def heap_reset(self) -> None:
+        self._heap_off = 0
+
+    # -- collectives ---------------------------------------------------------------------
+    @staticmethod
+    def _stream_ptr(stream) -> c_void_p:
+        import torch
+
+        s = torch.cuda.current_stream() if stream is None else stream
+        return c_void_p(s.cuda_stream)
+
+    def _active(self, active):
+        act = list(range(self.world)) if active is None else [int(a) for a in active]
+        return _int_array(act), len(act)
+
+    @staticmethod
+    def _dt(t) -> int:
+        return DTYPE_IDS[str(t.dtype).replace("torch.", "")]
+
+    def all_reduce(self, tensor, out=None, op: str = "sum", algo: str = "auto", wire: Optional[str] = None,
+                   active=None, stream=None):
+        out = tensor if out is None else out
+        dt = self._dt(tensor)
+        wd = dt if wire is None else DTYPE_IDS[wire]
+        arr, n = self._active(active)
+        _check(self.lib.adapcc_allreduce(self.handle, c_void_p(tensor.data_ptr()), c_void_p(out.data_ptr()),
+                                         tensor.numel(), dt, wd, OP_IDS[op], ALGO_IDS[algo], arr, n,
+                                         self._stream_ptr(stream)), "all_reduce")
+        return out
+
+    def reduce(self, tensor, root: int, out=None, op: str = "sum", algo: str = "auto",
+               wire: Optional[str] = None, active=None, stream=None):
+        out = tensor if out is None else out
+        dt = self._dt(tensor)
+        wd = dt if wire is None else DTYPE_IDS[wire]
+        arr, n = self._active(active)
+        _check(self.lib.adapcc_reduce(self.handle, c_void_p(tensor.data_ptr()), c_void_p(out.data_ptr()),
+                                      tensor.numel(), dt, wd, OP_IDS[op], ALGO_IDS[algo], int(root), arr, n,
+                                      self._stream_ptr(stream)), "reduce")
+        return out
+
+    def broadcast(self, tensor, root: int, active=None, stream=None):
+        arr, n = self._active(active)
+        _check(self.lib.adapcc_broadcast(self.handle, c_void_p(tensor.data_ptr()), tensor.numel(),
+                                         self._dt(tensor), int(root), arr, n, self._stream_ptr(stream)),
+               "broadcast")
+        return tensor
+
+    def tree_collective(self, prim: int, tensor, out=None, op: str = "sum", wire: Optional[str] = None,
+                        chunk_bytes: int = 1 << 20, active=None, stream=None):
+        out = tensor if out is None else out
+        dt = self._dt(tensor)
+        wd = dt if wire is None else DTYPE_IDS[wire]
+        arr, n = self._active(active)
+        _check(self.lib.adapcc_tree_collective(self.handle, int(prim), c_void_p(tensor.data_ptr()),
+                                               c_void_p(out.data_ptr()), tensor.numel(), dt, wd, OP_IDS[op],
+                                               int(chunk_bytes), arr, n, self._stream_ptr(stream)),
+               "tree_collective")
+        return out
+
+    def skip_op(self, stream=None) -> None:
+        _check(self.lib.adapcc_skip_op(self.handle, self._stream_ptr(stream)), "skip_op")
+
+    def check(self, stream=None) -> None:
+        """Synchronise the stream and raise if any device-side wait timed out."""
+        rc = self.lib.adapcc_ctx_check(self.handle, self._stream_ptr(stream))
+        if rc != 0:
+            raise NativeError(f"collective failed: {last_error()}")
+
+    def host_barrier(self) -> None:
+        _check(self.lib.adapcc_ctx_host_barrier(self.handle), "host_barrier")
+
+
+# ---- pure host queries (usable on the CPU-only box) -------------------------------------
+def native_relay_control(xml_text: str, world: int, tree: int, rank: int, active: Sequence[int]):
+    lib = load_library()
+    out = (c_int * 64)()
+    arr = _int_array(list(active))
+    n = lib.adapcc_relay_control(xml_text.encode(), world, tree, rank, arr, len(active), out, 64)
+    if n < 0:
+        raise NativeError(last_error())
+    return {"has_recv": bool(out[0]), "has_local": bool(out[1]), "has_kernel": bool(out[2]),
+            "has_send": bool(out[3]), "active_recvs": [out[5 + i] for i in range(out[4])], "n_trees": n}
+
+
+def native_tree_role(xml_text: str, world: int, tree: int, rank: int, active: Sequence[int], prim: int,
+                     relay_mode: int = 0):
+    lib = load_library()
+    out = (c_int * 64)()
+    arr = _int_array(list(active))
+    n = lib.adapcc_tree_role(xml_text.encode(), world, tree, rank, arr, len(active), prim, relay_mode, out, 64)
+    if n < 0:
+        raise NativeError(last_error())
+    return {"parent": out[0], "flags": out[1], "children": [out[3 + i] for i in range(out[2])], "n_trees": n}

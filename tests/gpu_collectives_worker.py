@@ -1,0 +1,296 @@
+"""Multi-rank worker for the native collective kernels (launched by torchrun or by
+tests/test_gpu_collectives.py). Checks every kernel variant against a plain fp32 PyTorch
+reference computed from all ranks' inputs (gathered with NCCL/gloo or regenerated from the
+shared seed), then optionally prints a small timing sweep.
+
+Usage: torchrun --nproc-per-node N tests/gpu_collectives_worker.py [--sweep] [--quick]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from adapcc_b200.constants import ALLREDUCE, BOARDCAST, REDUCE  # noqa: E402
+from adapcc_b200.runtime.native import NativeComm  # noqa: E402
+from adapcc_b200.runtime.rendezvous import unique_name  # noqa: E402
+
+
+def gen(rank, n, dtype, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed * 1000 + rank)
+    return (torch.randn(n, generator=g, dtype=torch.float32) * 2).to(dtype)
+
+
+def ref_reduce(world, n, dtype, seed, op, active, wire=None):
+    xs = [gen(r, n, dtype, seed) for r in active]
+    if wire is not None:
+        xs = [x.to(wire) for x in xs]
+    acc = torch.stack([x.float() for x in xs])
+    if op == "max":
+        return acc.max(0).values
+    s = acc.sum(0)
+    return s / len(active) if op == "avg" else s
+
+
+def tol(dtype, wire, n_active):
+    if (wire or dtype) in (torch.bfloat16,):
+        return 4e-2 * max(1, n_active) ** 0.5, 2e-2
+    if (wire or dtype) in (torch.float16,):
+        return 1e-2 * max(1, n_active) ** 0.5, 4e-3
+    return 1e-4, 1e-5
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    name = unique_name("worker")
+    comm = NativeComm(name, rank, world, local, staging_bytes=64 << 20, heap_bytes=128 << 20)
+    if rank == 0:
+        print(f"[worker] world={world} symm={comm.symm_backend} multicast={comm.multicast} "
+              f"heap_mc={comm.heap_multicast}", flush=True)
+    failures = []
+    n_checks = 0
+
+    def check(tag, got, want, dtype, wire, na):
+        nonlocal n_checks
+        n_checks += 1
+        atol, rtol = tol(dtype, wire, na)
+        got = got.float().cpu()
+        ok = torch.allclose(got, want, atol=atol, rtol=rtol)
+        if not ok:
+            err = (got - want).abs().max().item()
+            failures.append(f"rank {rank} {tag}: max err {err:.4g}")
+            print(f"[FAIL] rank {rank} {tag}: max err {err:.4g}", flush=True)
+
+    sizes = [1, 7, 1024, 4097, 65536 + 3, 1 << 20, (1 << 22) + 5]
+    if args.quick:
+        sizes = [7, 4097, (1 << 20) + 3]
+    algos = ["one_shot", "two_shot"] + (["nvls"] if comm.multicast else [])
+    all_ranks = list(range(world))
+    seed = 0
+    # ---- direct allreduce: algos x dtypes x ops x sizes ------------------------------
+    for dtype, wire in [(torch.float32, None), (torch.float32, "bfloat16"), (torch.bfloat16, None),
+                        (torch.float16, None)]:
+        wire_t = getattr(torch, wire) if wire else None
+        for op in ["sum", "avg", "max"]:
+            for algo in algos:
+                if algo == "nvls" and op == "max" and (wire_t or dtype) == torch.float32:
+                    continue
+                for n in sizes:
+                    seed += 1
+                    x = gen(rank, n, dtype, seed).to(dev)
+                    comm.all_reduce(x, op=op, algo=algo, wire=wire)
+                    comm.check()
+                    want = ref_reduce(world, n, dtype, seed, op, all_ranks, wire_t)
+                    check(f"allreduce {algo} {dtype} wire={wire} {op} n={n}", x, want, dtype, wire_t, world)
+    # out-of-place + auto
+    for n in sizes:
+        seed += 1
+        x = gen(rank, n, torch.float32, seed).to(dev)
+        y = torch.empty_like(x)
+        comm.all_reduce(x, out=y, op="sum", algo="auto")
+        comm.check()
+        check(f"allreduce auto oop n={n}", y, ref_reduce(world, n, torch.float32, seed, "sum", all_ranks),
+              torch.float32, None, world)
+        check(f"allreduce auto oop input intact n={n}", x, gen(rank, n, torch.float32, seed), torch.float32, None, 1)
+    # ---- zero-copy (symmetric heap) ----------------------------------------------------
+    for dtype in [torch.float32, torch.bfloat16]:
+        for algo in [a for a in algos if a != "one_shot"] + ["auto"]:
+            for n in [4096, (1 << 20) + 8]:
+                seed += 1
+                comm.heap_reset()
+                t = comm.symm_empty(n, dtype)
+                t.copy_(gen(rank, n, dtype, seed).to(dev))
+                torch.cuda.synchronize()
+                dist.barrier()
+                comm.all_reduce(t, op="avg", algo=algo)
+                comm.check()
+                check(f"zero-copy allreduce {algo} {dtype} n={n}", t,
+                      ref_reduce(world, n, dtype, seed, "avg", all_ranks), dtype, None, world)
+    # ---- reduce-to-root and broadcast (direct) ---------------------------------------
+    for root in sorted({0, world - 1}):
+        for algo in algos:
+            for n in [5, 70001]:
+                seed += 1
+                x = gen(rank, n, torch.float32, seed).to(dev)
+                comm.reduce(x, root=root, op="sum", algo=algo)
+                comm.check()
+                if rank == root:
+                    check(f"reduce {algo} root={root} n={n}", x,
+                          ref_reduce(world, n, torch.float32, seed, "sum", all_ranks), torch.float32, None, world)
+        for dtype in [torch.float32, torch.bfloat16]:
+            for n in [3, 70001]:
+                seed += 1
+                x = gen(rank, n, dtype, seed).to(dev)
+                comm.broadcast(x, root=root)
+                comm.check()
+                check(f"broadcast root={root} {dtype} n={n}", x, gen(root, n, dtype, seed).float(), dtype, None, 1)
+    # ---- active subsets ----------------------------------------------------------------
+    if world >= 3:
+        subsets = [[0, world - 1], list(range(1, world))]
+        for act in subsets:
+            for algo in ["one_shot", "two_shot"]:
+                seed += 1
+                n = 100003
+                x = gen(rank, n, torch.float32, seed).to(dev)
+                comm.all_reduce(x, op="avg", algo=algo, active=act)
+                comm.check()
+                want = ref_reduce(world, n, torch.float32, seed, "avg", act) if rank in act else gen(rank, n, torch.float32, seed)
+                check(f"subset {act} {algo}", x, want, torch.float32, None, len(act))
+    # ---- strategy trees ----------------------------------------------------------------
+    def chain_xml(order):
+        s = ""
+        for r in reversed(order[1:]):
+            s = f"<gpu id='{r}' ip='h'>{s}</gpu>"
+        return f"<root id='{order[0]}' ip='h'>{s}</root>"
+
+    def bin_xml(order):
+        def rec(i):
+            kids = "".join(rec(c) for c in (2 * i + 1, 2 * i + 2) if c < len(order))
+            tag = "root" if i == 0 else "gpu"
+            return f"<{tag} id='{order[i]}' ip='h'>{kids}</{tag}>"
+        return rec(0)
+
+    orders = [list(range(world)), list(reversed(range(world)))]
+    if world >= 4:
+        orders.append([(r * 3 + 1) % world for r in range(world)] if world % 3 else orders[0][1:] + orders[0][:1])
+    strategies = {
+        "chain2": "<trees>" + "".join(chain_xml(o) for o in orders[:2]) + "</trees>",
+        "binary": "<trees>" + "".join(bin_xml(o) for o in orders) + "</trees>",
+    }
+    for sname, xml in strategies.items():
+        ntrees = comm.load_strategy(xml)
+        for dtype, wire in [(torch.float32, None), (torch.float32, "bfloat16"), (torch.bfloat16, None)]:
+            wire_t = getattr(torch, wire) if wire else None
+            for n, chunk in [(16, 16), (70001, 4096), ((1 << 21) + 9, 1 << 18)]:
+                seed += 1
+                x = gen(rank, n, dtype, seed).to(dev)
+                comm.tree_collective(ALLREDUCE, x, op="sum", wire=wire, chunk_bytes=chunk)
+                comm.check()
+                # tree sums round partial results to the wire dtype at every hop
+                check(f"tree[{sname}] allreduce {dtype} wire={wire} n={n}", x,
+                      ref_reduce(world, n, dtype, seed, "sum", all_ranks, wire_t), dtype, wire_t or dtype, world * 2)
+        seed += 1
+        n = 50001
+        x = gen(rank, n, torch.float32, seed).to(dev)
+        comm.tree_collective(BOARDCAST, x, chunk_bytes=8192)
+        comm.check()
+        # tree t broadcasts slice t from ITS root
+        # (reference semantics: each tree owns one slice of the tensor)
+        import math
+        xml_roots = []
+        import re
+        for m in re.finditer(r"<root id='(\d+)'", xml):
+            xml_roots.append(int(m.group(1)))
+        epp = 4
+        npacks = math.ceil(n / epp)
+        per = math.ceil(npacks / ntrees)
+        want = torch.empty(n)
+        for t, r in enumerate(xml_roots):
+            lo, hi = min(t * per, npacks) * epp, min(min((t + 1) * per, npacks) * epp, n)
+            want[lo:hi] = gen(r, n, torch.float32, seed)[lo:hi]
+        check(f"tree[{sname}] boardcast n={n}", x, want, torch.float32, None, 1)
+        seed += 1
+        x = gen(rank, n, torch.float32, seed).to(dev)
+        comm.tree_collective(REDUCE, x, op="sum", chunk_bytes=8192)
+        comm.check()
+        full = ref_reduce(world, n, torch.float32, seed, "sum", all_ranks)
+        mine = gen(rank, n, torch.float32, seed)
+        for t, r in enumerate(xml_roots):
+            lo, hi = min(t * per, npacks) * epp, min(min((t + 1) * per, npacks) * epp, n)
+            if r == rank:
+                mine[lo:hi] = full[lo:hi]
+        check(f"tree[{sname}] reduce n={n}", x, mine, torch.float32, None, world)
+        # relay control: forward and bypass modes over an active subset
+        if world >= 3:
+            act = [0, world - 1]
+            for mode in (0, 1):
+                comm.set_tunable("relay_mode", mode)
+                seed += 1
+                x = gen(rank, n, torch.float32, seed).to(dev)
+                comm.tree_collective(ALLREDUCE, x, op="avg", chunk_bytes=8192, active=act)
+                comm.check()
+                want = ref_reduce(world, n, torch.float32, seed, "avg", act) if rank in act else gen(rank, n, torch.float32, seed)
+                check(f"tree[{sname}] relay mode={mode} active={act}", x, want, torch.float32, None, 2)
+            comm.set_tunable("relay_mode", 0)
+
+    torch.cuda.synchronize()
+    dist.barrier()
+    fl = [None] * world
+    dist.all_gather_object(fl, failures)
+    all_fail = [f for sub in fl for f in sub]
+    if rank == 0:
+        print(f"[worker] checks per rank: {n_checks}; failures: {len(all_fail)}", flush=True)
+        for f in all_fail[:40]:
+            print("   ", f)
+
+    # ---- timing sweep ------------------------------------------------------------------
+    results = []
+    if args.sweep:
+        comm.load_strategy(strategies["binary"])
+        big = comm.symm_empty if False else None
+        sweep_sizes = [1 << p for p in range(10, 28, 2 if args.quick else 1)]  # bytes
+        def timeit(fn, iters, warm=5):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize(); dist.barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(iters):
+                fn()
+            e.record(); torch.cuda.synchronize()
+            t = torch.tensor([s.elapsed_time(e) / iters], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item() * 1e-3
+        for nbytes in sweep_sizes:
+            n = nbytes // 4
+            x = torch.randn(n, device=dev)
+            comm.heap_reset()
+            hz = comm.symm_empty(n, torch.float32) if nbytes <= comm.heap_bytes else None
+            iters = 50 if nbytes <= (1 << 22) else 15
+            row = {"bytes": nbytes}
+            row["nccl"] = timeit(lambda: dist.all_reduce(x), iters)
+            for algo in algos + ["auto"]:
+                if algo == "one_shot" and nbytes > (4 << 20):
+                    continue
+                row[algo] = timeit(lambda: comm.all_reduce(x, algo=algo), iters)
+                if hz is not None and algo not in ("one_shot",):
+                    row[algo + "_zc"] = timeit(lambda: comm.all_reduce(hz, algo=algo), iters)
+            row["bf16wire_auto"] = timeit(lambda: comm.all_reduce(x, algo="auto", wire="bfloat16"), iters)
+            if nbytes >= (1 << 16):
+                row["tree"] = timeit(lambda: comm.tree_collective(ALLREDUCE, x, chunk_bytes=max(16, min(1 << 20, nbytes // 8))), iters)
+            comm.check()
+            results.append(row)
+            if rank == 0:
+                f = 2 * (world - 1) / world
+                print("[sweep] %10d B " % nbytes + " ".join(
+                    f"{k}={v * 1e6:8.1f}us({nbytes * f / v / 1e9:6.1f}GB/s)" for k, v in row.items() if k != "bytes"),
+                    flush=True)
+    if rank == 0 and args.out:
+        os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+        with open(args.out, "w") as fh:
+            json.dump({"world": world, "symm": comm.symm_backend, "multicast": comm.multicast,
+                       "checks": n_checks, "failures": all_fail, "sweep": results}, fh, indent=1)
+    dist.barrier()
+    comm.close()
+    dist.destroy_process_group()
+    sys.exit(1 if all_fail else 0)
+
+
+if __name__ == "__main__":
+    main()
