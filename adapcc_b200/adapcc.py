@@ -1,0 +1,99 @@
+"""High-level API: the ``AdapCC`` class-level singleton.
+
+Same surface as /root/reference/adapcc.py:6-76 — ``init(args, local_rank, world_rank, world_size)``,
+``setup(prim)``, ``allreduce/reduce/boardcast/alltoall``, ``reconstruct_topology(args, prim)``,
+``set_profile_freq``, ``clear(prim)`` and the ``communicator`` attribute — so a training script
+written for the reference (see /root/reference/train_ddp.py:30-58) only changes its import.
+
+``args`` needs: ``port, strategy_file, logical_graph, entry_point, parallel_degree, profile_freq``
+(optional extras: ``backend, algo, wire_dtype, reduce_op, relay_mode, relay_control, policy,
+staging_mb, heap_mb, work_dir``). ``entry_point``: 6 = detect + profile + synthesise,
+7 = profile + synthesise, -1 = use the given strategy file as is.
+"""
+from __future__ import annotations
+
+from .commu import CudaCommu
+from .constants import (ALLGATHER, ALLREDUCE, ALLTOALL, BOARDCAST, DETECT, PROFILE, REDUCE,  # noqa: F401
+                        REDUCESCATTER)
+
+
+class AdapCC:
+    # meta info since the first registered
+    communicator_path = None            # resolved lazily: adapcc_b200/_C/libadapcc.so
+    communicator: CudaCommu = None
+    local_rank = None
+    world_rank = None
+    world_size = None
+    profile_freq = None
+
+    @classmethod
+    def init(cls, args, local_rank, world_rank, world_size):
+        dylib = None
+        if getattr(args, "backend", "nccl") != "gloo":
+            try:
+                import torch
+
+                if torch.cuda.is_available():
+                    from .runtime.native import lib_path, load_library
+
+                    dylib = load_library()
+                    cls.communicator_path = str(lib_path())
+            except ImportError:
+                dylib = None
+        cls.communicator = CudaCommu(args, dylib, local_rank, world_rank, world_size)
+        cls.local_rank, cls.world_rank, cls.world_size = local_rank, world_rank, world_size
+        cls.profile_freq = getattr(args, "profile_freq", None)
+
+        entry = getattr(args, "entry_point", -1)
+        if entry == DETECT:
+            cls.communicator.init_threads(DETECT)
+            cls.communicator.exit_threads(DETECT)
+            cls.communicator.init_threads(PROFILE)
+            cls.communicator.exit_threads(PROFILE)
+        elif entry == PROFILE:
+            cls.communicator.init_threads(PROFILE)
+            cls.communicator.exit_threads(PROFILE)
+        elif entry == -1 or entry is None:
+            pass
+        else:
+            print("no supported entry point for init.")
+
+    @classmethod
+    def setup(cls, prim):
+        cls.communicator.init_threads(prim)
+
+    @classmethod
+    def allreduce(cls, tensor, size=None, chunk_bytes=None, active_gpus=None):
+        return cls.communicator.all_reduce(tensor, size, chunk_bytes, active_gpus)
+
+    @classmethod
+    def reduce(cls, tensor, size=None, chunk_bytes=None, active_gpus=None):
+        return cls.communicator.reduce(tensor, size, chunk_bytes, active_gpus)
+
+    @classmethod
+    def boardcast(cls, tensor, size=None, chunk_bytes=None):
+        return cls.communicator.boardcast(tensor, size, chunk_bytes)
+
+    @classmethod
+    def alltoall(cls, tensor, size=None, chunk_bytes=None):
+        """The reference declares this primitive but forwards to a method that does not exist
+        (/root/reference/adapcc.py:59-61, latent AttributeError). Here it is a real dense
+        all-to-all of equal splits, carried by the expert-parallel dispatch kernels."""
+        from .parallel.alltoall import all_to_all_single
+
+        return all_to_all_single(cls.communicator, tensor, size)
+
+    @classmethod
+    def reconstruct_topology(cls, args, prim):
+        cls.clear(prim)
+        cls.init(args, cls.local_rank, cls.world_rank, cls.world_size)
+        cls.setup(prim)
+
+    @classmethod
+    def set_profile_freq(cls, freq):
+        cls.profile_freq = freq
+
+    @classmethod
+    def clear(cls, prim):
+        cls.communicator.exit_threads(prim)
+        cls.communicator.clear()

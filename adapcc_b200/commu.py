@@ -1,0 +1,531 @@
+"""Control plane + data-plane front end (``CudaCommu``).
+
+API and workflow parity with /root/reference/commu.py:40-435:
+
+* primitive ids, ``init_threads`` / ``exit_threads`` workflow DETECT -> PROFILE -> SYNTHESIS ->
+  transmission-context setup, ``all_reduce`` / ``reduce`` / ``boardcast``, ``update_relay``,
+  ``cuda_allreduce_hook`` (torch DDP communication hook), ``clear``;
+* rank 0 hosts the gRPC coordinator, every rank runs a controller thread that heartbeats once per
+  step and drives relays.
+
+What changed (B200-first):
+
+* a collective is ONE asynchronous kernel launch on a CUDA stream (no background pthread blocked
+  inside ``initThreads``, no ``time.sleep(3)`` hand-shake, no blocking ``ctypes`` call);
+* the DDP hook runs the collective on a high-priority side stream and returns a real CUDA future,
+  so gradient communication overlaps the rest of backward (the reference blocks the autograd
+  thread, commu.py:385-435); gradients are averaged over the active ranks inside the kernel
+  (the reference returns the unscaled sum);
+* the algorithm is chosen per message from the profiled alpha/beta (one-shot, two-shot, NVLS or the
+  strategy's trees); fp32 buckets can travel as bf16 on the wire, cast fused into the kernel;
+* CPU tensors (``--backend gloo``) run the same strategy through the reference executor.
+"""
+from __future__ import annotations
+
+import json
+import os
+import threading
+import time
+from queue import Empty, Queue
+from types import SimpleNamespace
+from typing import List, Optional
+
+from . import topology as topo
+from .constants import (ALLGATHER, ALLREDUCE, ALLTOALL, BOARDCAST, DETECT, PROFILE, REDUCE, REDUCESCATTER,
+                        RELAY_BYPASS, RELAY_FORWARD)
+from .coord import Controller, Coordinator, Hooker, make_server
+from .dispatcher import Dispatcher
+from .strategy import Strategy, default_chunk_bytes
+from .synth import LinkModel, Synthesizer, crossover_bytes
+
+__all__ = ["CudaCommu", "ALLREDUCE", "REDUCE", "BOARDCAST", "ALLGATHER", "ALLTOALL", "REDUCESCATTER", "DETECT",
+           "PROFILE"]
+
+_DATA_PRIMS = (ALLREDUCE, REDUCE, BOARDCAST)
+
+
+def _arg(args, name, default):
+    v = getattr(args, name, None)
+    return default if v is None else v
+
+
+class CudaCommu:
+    def __init__(self, args, dylib, local_rank, world_rank, world_size):
+        self.args = args
+        self.dylib = dylib                      # kept for signature parity; ctypes handle or None
+        self.local_rank, self.world_rank, self.world_size = local_rank, world_rank, world_size
+        self.port = int(_arg(args, "port", 5000))
+        self.init_count = 0
+        self.work_dir = os.path.abspath(_arg(args, "work_dir", os.getcwd()))
+        self.topo_dir = os.path.join(self.work_dir, "topology")
+        os.makedirs(self.topo_dir, exist_ok=True)
+
+        # ---- ip table (one line per rank; generated for single-node jobs) -----------------
+        self.ip_table_file = os.path.join(self.topo_dir, "ip_table.txt")
+        if os.path.exists(self.ip_table_file):
+            self.ip_table = topo.read_ip_table(self.ip_table_file)
+        else:
+            self.ip_table = []
+        if len(self.ip_table) != world_size:
+            self.ip_table = [os.environ.get("ADAPCC_NODE_IP", "127.0.0.1")] * world_size
+            if world_rank == 0:
+                topo.write_ip_table(self.ip_table_file, self.ip_table)
+        self.dispatcher = Dispatcher(self.ip_table)
+        self.single_server = len(set(self.ip_table)) == 1
+
+        # ---- data-plane policy -----------------------------------------------------------------
+        self.algo = _arg(args, "algo", os.environ.get("ADAPCC_ALGO", "auto"))
+        self.wire_dtype = _arg(args, "wire_dtype", os.environ.get("ADAPCC_WIRE_DTYPE"))   # e.g. "bfloat16"
+        self.reduce_op = _arg(args, "reduce_op", "avg")       # DDP hook; primitives default to "sum"
+        self.relay_mode = RELAY_BYPASS if str(_arg(args, "relay_mode", "forward")) in ("bypass", "1") else RELAY_FORWARD
+        self.is_bsp = bool(_arg(args, "bsp", True))
+        self.relay_control = bool(_arg(args, "relay_control", True)) and world_size > 1
+        self.staging_bytes = int(_arg(args, "staging_mb", os.environ.get("ADAPCC_STAGING_MB", 256))) << 20
+        self.heap_bytes = int(_arg(args, "heap_mb", os.environ.get("ADAPCC_HEAP_MB", 0))) << 20
+        self.verbose = bool(int(os.environ.get("ADAPCC_VERBOSE", "0")))
+
+        self.active_gpus = list(range(world_size))
+        self.chunk_bytes: Optional[int] = None
+        self.strategy: Optional[Strategy] = None
+        self.link_model: Optional[LinkModel] = None
+        self.synthesizer = Synthesizer(strategy_file=_arg(args, "strategy_file", None), ip_table=self.ip_table,
+                                       parallel_degree=int(_arg(args, "parallel_degree", 4)),
+                                       policy=_arg(args, "policy", "par-trees"),
+                                       intra_policy=_arg(args, "intra_policy", "binary" if self.single_server else "chain"))
+        self.native = None                      # NativeComm, created on first GPU context
+        self._open_prims = set()
+        self._comm_stream = None
+        self._relay_stream = None
+
+        # ---- coordinator (rank 0) + clients ------------------------------------------------------
+        self.coordinator: Optional[Coordinator] = None
+        self.server = None
+        self.coordinator_port = int(_arg(args, "coordinator_port", os.environ.get("ADAPCC_COORD_PORT", 50051)))
+        self.controller: Optional[Controller] = None
+        self.hooker: Optional[Hooker] = None
+        if self.relay_control:
+            if world_rank == 0:
+                self.coordinator = Coordinator(self.ip_table[0], self.coordinator_port, world_size,
+                                               relay_threshold=float(_arg(args, "relay_threshold", 0.1)),
+                                               fault_tolerant_time=float(_arg(args, "fault_tolerant_time", 10.0)))
+                self.server = make_server(self.coordinator)
+                self.server.start()
+            self.controller = Controller(self.ip_table[0], self.coordinator_port)
+            self.hooker = Hooker(self.ip_table[0], self.coordinator_port)
+
+        # ---- controller agent ---------------------------------------------------------------------
+        self.step_queue: Queue = Queue()
+        self.relay_signal_queue: Queue = Queue()
+        self.bsp_queue: Queue = Queue()
+        self.relay_results: List = []
+        self.current_step = 0
+        self.local_hook_num = 0
+        self.bucket_info: List = []             # (numel, chunk_bytes, dtype) per bucket, recorded at step 1
+        self.relay_buffer: List = []
+        self.accumulated_bw = 0.0
+        self.fault_worker_list: List[int] = []
+        self.stats = {"hook_rpc_s": [], "relay_steps": 0, "ops": 0}
+        self._lock = threading.Lock()
+        self.controller_thread = threading.Thread(target=self._controller_thread_func, daemon=True,
+                                                  name=f"adapcc-controller-{world_rank}")
+        self.controller_thread.start()
+
+    # ==========================================================================================
+    # helpers
+    # ==========================================================================================
+    def _log(self, msg: str) -> None:
+        if self.verbose:
+            print(f"[Rank {self.world_rank}]{msg}", flush=True)
+
+    def _barrier(self) -> None:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+        elif self.native is not None:
+            self.native.host_barrier()
+
+    def _use_cuda(self) -> bool:
+        import torch
+
+        return torch.cuda.is_available() and _arg(self.args, "backend", "nccl") != "gloo"
+
+    def _ensure_native(self):
+        if self.native is None:
+            from .runtime.native import NativeComm
+            from .runtime.rendezvous import unique_name
+
+            name = unique_name(f"adapcc-{self.port}-{self.init_count}")
+            self.native = NativeComm(name, self.world_rank, self.world_size, self.local_rank,
+                                     staging_bytes=self.staging_bytes, heap_bytes=self.heap_bytes)
+            self.native.set_tunable("relay_mode", self.relay_mode)
+            self._apply_tunables()
+        return self.native
+
+    def _streams(self):
+        import torch
+
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.local_rank, priority=-1)
+            self._relay_stream = torch.cuda.Stream(device=self.local_rank, priority=-1)
+        return self._comm_stream, self._relay_stream
+
+    def _tunables_path(self) -> str:
+        return os.path.join(self.topo_dir, "tunables.json")
+
+    def _apply_tunables(self) -> None:
+        """Per-message algorithm thresholds derived from the last profile (rank 0 wrote them)."""
+        if self.native is None or not os.path.exists(self._tunables_path()):
+            return
+        try:
+            with open(self._tunables_path()) as f:
+                t = json.load(f)
+            for k in ("one_shot_max_bytes", "nvls_min_bytes", "max_blocks", "tree_blocks", "nvls_min_ranks"):
+                if k in t:
+                    self.native.set_tunable(k, int(t[k]))
+        except (OSError, ValueError) as e:
+            self._log(f"ignoring unreadable tunables: {e}")
+
+    def _load_strategy(self) -> None:
+        path = _arg(self.args, "strategy_file", None)
+        if path and os.path.exists(path):
+            self.strategy = Strategy.from_file(path, self.world_size)
+            if self.chunk_bytes is None and "chunk" in self.strategy.attrs:
+                try:
+                    self.chunk_bytes = int(self.strategy.attrs["chunk"])
+                except ValueError:
+                    pass
+        elif self.strategy is None:
+            from .strategy import make_strategy
+
+            self.strategy = make_strategy(self.world_size, min(int(_arg(self.args, "parallel_degree", 4)),
+                                                               self.world_size), "binary", self.ip_table)
+
+    # ==========================================================================================
+    # controller thread (relay driver + heartbeat)
+    # ==========================================================================================
+    def _controller_thread_func(self):
+        while True:
+            step = self.step_queue.get()
+            if step == -1:
+                break
+            if not self.relay_control:
+                continue
+            try:
+                active, status = self.controller.send_relay_request(step, self.world_rank)
+            except Exception as e:  # noqa: BLE001  (coordinator gone: stop heartbeating)
+                self._log(f"controller RPC failed: {e}")
+                return
+            if status == 0:
+                self.fault_worker_list = [w for w in range(self.world_size) if w not in active]
+                print(f"Fault occurs: rank {self.world_rank} alive; missing {self.fault_worker_list}", flush=True)
+                self.bsp_queue.put(step)
+                return
+            self.active_gpus = sorted(active)
+            self._log(f"Controller active: {active}")
+            if step <= 1:
+                continue
+            if self.world_rank not in active:
+                self.stats["relay_steps"] += 1
+                self._run_as_relay(step, sorted(active))
+                self.bsp_queue.put(step)
+
+    def _run_as_relay(self, step: int, active: List[int]) -> None:
+        """This rank missed the step's deadline: keep the data plane going for the others."""
+        if self.native is None or not self.bucket_info:
+            return
+        import torch
+
+        _, relay_stream = self._streams()
+        with torch.cuda.device(self.local_rank), torch.cuda.stream(relay_stream):
+            for i, (numel, chunk_bytes, dtype) in enumerate(self.bucket_info):
+                if self._resolve_algo(numel, dtype, active) == "tree" and self.relay_mode == RELAY_FORWARD:
+                    buf = self.relay_buffer[i]
+                    self.native.tree_collective(ALLREDUCE, buf[:numel], op=self.reduce_op, wire=self._wire_for(dtype),
+                                                chunk_bytes=chunk_bytes, active=active)
+                    self.relay_results.append(buf)
+                else:
+                    self.native.skip_op()       # direct algorithms never route through a relay
+                self.relay_signal_queue.put(step)
+        relay_stream.synchronize()
+
+    # ==========================================================================================
+    # workflow
+    # ==========================================================================================
+    def clear(self):
+        """stop the controller and the grpc server"""
+        self.update_relay(-1)
+        if self.controller_thread.is_alive():
+            self.controller_thread.join(timeout=5)
+        for c in (self.controller, self.hooker):
+            if c is not None:
+                c.close()
+        if self.server is not None:
+            self.server.stop(1)
+            self.server = None
+        if self.native is not None:
+            self._barrier()
+            self.native.close()
+            self.native = None
+
+    def update_relay(self, step):
+        """called once per iteration before forward: heartbeat + (for relays) data-plane duty"""
+        self.step_queue.put(step)
+        self.current_step = step
+        self.local_hook_num = 0
+
+    def init_threads(self, prim):
+        if prim == DETECT:
+            self._detect()
+        elif prim == PROFILE:
+            self._profile()
+        elif prim in _DATA_PRIMS:
+            self._load_strategy()
+            if self._use_cuda():
+                t0 = time.time()
+                n = self._ensure_native()
+                if self.strategy is not None:
+                    n.load_strategy(self.strategy.to_xml())
+                self._log("transmission context setup time=%6.2f(ms)" % ((time.time() - t0) * 1e3))
+            self._open_prims.add(prim)
+        else:
+            raise NotImplementedError(f"primitive {prim} is not implemented (the reference implements 0,1,2,6,7)")
+        self.init_count += 1
+
+    def exit_threads(self, prim):
+        if prim == DETECT:
+            if self.local_rank == 0:
+                self.dispatcher.dispatch_detected_topo(os.path.join(self.topo_dir, "topo_detect*"), self.topo_dir)
+            self._barrier()
+            if self.local_rank == 0:
+                self._gather_detect_graph()
+            self._barrier()
+        elif prim == PROFILE:
+            if self.local_rank == 0:
+                self.dispatcher.send_profiled_topo(os.path.join(self.topo_dir, "topo_profile*"), self.topo_dir)
+            self._barrier()
+            if self.world_rank == 0:
+                lc_graph, bw_graph = self._gather_topo_profile()
+                self._synthesis_strategy(lc_graph, bw_graph)
+                sf = _arg(self.args, "strategy_file", None)
+                if sf:
+                    self.dispatcher.dispatch_strategy(sf, os.path.dirname(os.path.abspath(sf)))
+            self._barrier()
+            self._apply_tunables()
+        elif prim in _DATA_PRIMS:
+            self._open_prims.discard(prim)
+            if self.native is not None:
+                import torch
+
+                torch.cuda.synchronize(self.local_rank)
+
+    # -- DETECT -----------------------------------------------------------------------------------
+    def _detect(self):
+        if self.local_rank != 0:
+            return
+        path = os.path.join(self.topo_dir, f"topo_detect_{self.world_rank}.xml")
+        xml = None
+        if self._use_cuda():
+            import ctypes
+
+            from .runtime.native import last_error, load_library
+
+            lib = load_library()
+            buf = ctypes.create_string_buffer(1 << 20)
+            n = lib.adapcc_detect_topology(self.world_rank, buf, len(buf))
+            if n < 0:
+                raise RuntimeError(f"topology detection failed: {last_error()}")
+            xml = buf.value.decode()
+        else:
+            g = sum(1 for ip in self.ip_table if ip == self.ip_table[self.world_rank])
+            gpus = "".join(f'<gpu id="{i}"/>' for i in range(g))
+            xml = f'<topology first_rank="{self.world_rank}" gpus="{g}" nvml="0"><cpu numa="0"><pcie root="cpu">{gpus}</pcie></cpu></topology>\n'
+        with open(path, "w") as f:
+            f.write(xml)
+
+    def _gather_detect_graph(self):
+        from .strategy import xmlio
+
+        r0s = topo.local_rank0_list(self.ip_table)
+        groups = topo.server_groups(self.ip_table)
+        files = [os.path.join(self.topo_dir, f"topo_detect_{r}.xml") for r in r0s]
+        graph = topo.build_logical_graph(files, [self.ip_table[r] for r in r0s], r0s,
+                                         [len(groups[r]) for r in r0s])
+        lg = _arg(self.args, "logical_graph", os.path.join(self.topo_dir, "logical_graph.xml"))
+        os.makedirs(os.path.dirname(os.path.abspath(lg)), exist_ok=True)
+        xmlio.dump_file(graph, lg)
+
+    # -- PROFILE ----------------------------------------------------------------------------------
+    def _profile(self):
+        path = os.path.join(self.topo_dir, f"topo_profile_{self.world_rank}")
+        w = self.world_size
+        if self._use_cuda() and w > 1:
+            import ctypes
+
+            import torch
+
+            from .runtime.native import last_error
+
+            n = self._ensure_native()
+            F = ctypes.c_float * w
+            lat, rd, wr, nv = F(), F(), F(), ctypes.c_float(0)
+            n.lib.adapcc_profile_links.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_int, F, F, F,
+                                                   ctypes.POINTER(ctypes.c_float), ctypes.c_void_p]
+            probe = int(os.environ.get("ADAPCC_PROFILE_MB", 64)) << 20
+            with torch.cuda.device(self.local_rank):
+                rc = n.lib.adapcc_profile_links(n.handle, probe, 64, lat, rd, wr, ctypes.byref(nv),
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            if rc != 0:
+                raise RuntimeError(f"link profiling failed: {last_error()}")
+            topo.write_profile(path, self.world_rank, w, list(lat), list(rd), list(wr), float(nv.value))
+        else:
+            lat = [0.0 if d == self.world_rank else 50.0 for d in range(w)]
+            bw = [0.0 if d == self.world_rank else 1.0 for d in range(w)]
+            topo.write_profile(path, self.world_rank, w, lat, bw)
+
+    def _gather_topo_profile(self):
+        files = [os.path.join(self.topo_dir, f"topo_profile_{r}") for r in range(self.world_size)]
+        lc_graph, bw_graph, ext = topo.read_profiles(files, self.world_size)
+        self.accumulated_bw = topo.accumulated_bandwidth(bw_graph)
+        self._profile_ext = ext
+        return lc_graph, bw_graph
+
+    def _synthesis_strategy(self, lc_graph, bw_graph):
+        self.synthesizer.set_ip_info(self.ip_table)
+        self.synthesizer.set_parallel_degree(int(_arg(self.args, "parallel_degree", 4)))
+        self.synthesizer.set_latency_graph(lc_graph)
+        self.synthesizer.set_bandwidth_graph(bw_graph)
+        self.chunk_bytes = self.synthesizer.generate_strategy("reduce")
+        self.link_model = LinkModel(lc_graph, bw_graph)
+        if self.coordinator is not None and self.accumulated_bw > 0:
+            self.coordinator.set_traffic(self.coordinator.accumulated_size, self.accumulated_bw)
+        ext = getattr(self, "_profile_ext", {"nvls": []})
+        nvls = max(ext.get("nvls", [0.0]) or [0.0])
+        tun = {
+            "one_shot_max_bytes": min(max(crossover_bytes(self.link_model, "one_shot", "two_shot", nvls=False), 16 << 10),
+                                      4 << 20),
+            "nvls_bw_gbs": nvls,
+            "p2p_bw_gbs": self.link_model.min_bw(),
+            "alpha_us": self.link_model.mean_alpha() * 1e6,
+        }
+        with open(self._tunables_path(), "w") as f:
+            json.dump(tun, f, indent=1)
+
+    # ==========================================================================================
+    # data plane
+    # ==========================================================================================
+    def _wire_for(self, dtype) -> Optional[str]:
+        import torch
+
+        if self.wire_dtype and dtype == torch.float32:
+            return self.wire_dtype
+        return None
+
+    def _resolve_algo(self, numel, dtype, active) -> str:
+        """'tree' when the strategy must be honoured hop by hop (multi-server, or explicitly asked),
+        otherwise a direct algorithm picked per message by the native runtime."""
+        if self.algo != "auto":
+            return self.algo
+        if self.strategy is not None and self.strategy.attrs.get("algo") in ("tree", "one_shot", "two_shot", "nvls"):
+            return self.strategy.attrs["algo"]
+        return "auto" if self.single_server else "tree"
+
+    def _collective(self, prim, buffer, size, chunk_bytes, active_gpus, op, root=None):
+        import torch
+
+        size = int(buffer.numel() if size is None else size)
+        active = sorted(set(self.active_gpus if active_gpus is None else [int(a) for a in active_gpus]))
+        flat = buffer.view(-1)[:size] if size != buffer.numel() else buffer.view(-1)
+        if chunk_bytes is None:
+            chunk_bytes = self.chunk_bytes or default_chunk_bytes(size * buffer.element_size())
+        self.stats["ops"] += 1
+        if not buffer.is_cuda:
+            from .strategy.cpu_executor import tree_collective_cpu
+
+            if self.strategy is None:
+                self._load_strategy()
+            tree_collective_cpu(prim, flat, self.strategy, self.world_rank, self.world_size, active=active, op=op,
+                                chunk_bytes=int(chunk_bytes), relay_mode=self.relay_mode)
+            return buffer
+        n = self._ensure_native()
+        algo = self._resolve_algo(size, buffer.dtype, active)
+        wire = self._wire_for(buffer.dtype)
+        if algo == "tree":
+            n.tree_collective(prim, flat, op=op, wire=wire, chunk_bytes=int(chunk_bytes), active=active)
+        elif prim == ALLREDUCE:
+            n.all_reduce(flat, op=op, algo=algo, wire=wire, active=active)
+        elif prim == REDUCE:
+            n.reduce(flat, root=(active[0] if root is None else root), op=op, algo=algo, wire=wire, active=active)
+        else:
+            n.broadcast(flat, root=(active[0] if root is None else root), active=active)
+        return buffer
+
+    # @buffer: torch tensor (device or host), @size: number of elements, @chunk_bytes: pipelining
+    # granularity in bytes, @active_gpus: world ranks taking part (reference signature).
+    def all_reduce(self, buffer, size=None, chunk_bytes=None, active_gpus=None, op="sum"):
+        return self._collective(ALLREDUCE, buffer, size, chunk_bytes, active_gpus, op)
+
+    def reduce(self, buffer, size=None, chunk_bytes=None, active_gpus=None, op="sum", root=None):
+        return self._collective(REDUCE, buffer, size, chunk_bytes, active_gpus, op, root)
+
+    def boardcast(self, buffer, size=None, chunk_bytes=None, active_gpus=None, root=None):
+        return self._collective(BOARDCAST, buffer, size, chunk_bytes, active_gpus, "sum", root)
+
+    broadcast = boardcast
+
+    def synchronize(self):
+        """Wait for the data plane and raise if a device-side wait timed out."""
+        if self.native is not None:
+            import torch
+
+            for s in (self._comm_stream, self._relay_stream, torch.cuda.current_stream(self.local_rank)):
+                if s is not None:
+                    self.native.check(s)
+
+    # ==========================================================================================
+    # DDP communication hook
+    # ==========================================================================================
+    def cuda_allreduce_hook(self, state: object, bucket):
+        import torch
+
+        if self.local_hook_num == 0 and self.relay_control:
+            t0 = time.time()
+            self.active_gpus = sorted(self.hooker.send_ready_request(self.current_step, self.world_rank))
+            self.stats["hook_rpc_s"].append(time.time() - t0)
+        self.local_hook_num += 1
+        buffer = bucket.buffer()
+        size = int(buffer.numel())
+        total_bytes = buffer.element_size() * size
+        chunk_bytes = default_chunk_bytes(total_bytes)
+        self._log(f"hook active: {self.active_gpus}; tensor number {size}, {total_bytes} bytes, chunk bytes {chunk_bytes}")
+
+        if not buffer.is_cuda:
+            self.all_reduce(buffer, size, chunk_bytes, self.active_gpus, op=self.reduce_op)
+            fut = torch.futures.Future()
+            fut.set_result(buffer)
+            return fut
+
+        active = self.active_gpus
+        i_am_active = self.world_rank in active
+        if self.current_step == 1:
+            self.bucket_info.append((size, chunk_bytes, buffer.dtype))
+            if self.relay_control and self.relay_mode == RELAY_FORWARD and self._resolve_algo(size, buffer.dtype, active) == "tree":
+                self.relay_buffer.append(torch.zeros(size, dtype=buffer.dtype, device=buffer.device))
+            else:
+                self.relay_buffer.append(None)
+        comm_stream, _ = self._streams()
+        comm_stream.wait_stream(torch.cuda.current_stream(buffer.device))
+        with torch.cuda.stream(comm_stream):
+            if i_am_active or self.current_step <= 1:
+                self.all_reduce(buffer, size, chunk_bytes, active if self.current_step > 1 else list(range(self.world_size)),
+                                op=self.reduce_op)
+            # relays (BSP): this rank's own un-reduced gradient is used for its local update; the
+            # controller thread keeps the data plane consistent (skip / forward) on the relay stream
+            fut = torch.futures.Future(devices=[buffer.device])
+            fut.set_result(buffer)
+        if not i_am_active and self.current_step > 1 and self.local_hook_num == max(1, len(self.bucket_info)):
+            try:
+                self.bsp_queue.get(timeout=60)
+            except Empty:
+                pass
+        return fut

@@ -24,4 +24,4 @@ RELAY_FORWARD = 0   # reference semantics: inactive ranks on a path forward data
 RELAY_BYPASS = 1    # NVSwitch-aware: inactive ranks are contracted out of the trees
 
 # TreeRoleFlags (csrc/common.h)
-TR_HAS_LOCAL, TR_IN_REDUCE, TR_IN_BCAST, TR_WANT_RESULT, TR_PUBLISH = 1, 2, 4, 8, 16
+TR_HAS_LOCAL, TR_IN_REDUCE, TR_IN_BCAST, TR_WANT_RESULT, TR_PUBLISH, TR_PARENT_IS_ROOT = 1, 2, 4, 8, 16, 32

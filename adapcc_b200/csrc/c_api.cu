@@ -61,7 +61,7 @@ void* adapcc_ctx_peer_staging_ptr(void* h, int r) { return static_cast<CommConte
 int adapcc_ctx_last_algo(void* h) { return static_cast<CommContext*>(h)->last_algo; }
 
 // keys: 0 max_blocks, 1 one_shot_max_bytes, 2 nvls_min_bytes, 3 relay_mode, 4 timeout_ms,
-// 5 tree_blocks
+// 5 tree_blocks, 6 tree_chunk_max_bytes
 int adapcc_ctx_set_tunable(void* h, int key, long long value) {
   CommContext* c = static_cast<CommContext*>(h);
   switch (key) {
@@ -71,6 +71,8 @@ int adapcc_ctx_set_tunable(void* h, int key, long long value) {
     case 3: c->tun.relay_mode = (int)value; break;
     case 4: c->tun.timeout_ms = value; break;
     case 5: c->tun.tree_blocks = (int)std::max<long long>(1, std::min<long long>(value, kMaxBlocks)); break;
+    case 6: c->tun.tree_chunk_max_bytes = value; break;
+    case 7: c->tun.nvls_min_ranks = (int)value; break;
     default: set_error("unknown tunable %d", key); return -1;
   }
   return 0;

@@ -11,10 +11,11 @@ namespace {
 constexpr size_t kPadBytes = 16384;                       // barrier pad region
 constexpr size_t kFlagOffset = kPadBytes;                 // chunk flags follow
 constexpr size_t kSigBytes = 65536;
-constexpr size_t kStateEpoch = 0, kStateTicket = 1024, kStateErr = 1028, kStateSeq = 1032,
-                 kStateBytes = 4096;
+constexpr size_t kStateEpoch = 0, kStateTicket = 12288, kStateErr = 12292, kStateSeq = 12296,
+                 kStateBytes = 16384;
+static_assert(kMaxBlocks * kMaxRanks * 4 <= kStateTicket, "epoch table too small");
 static_assert(kMaxBlocks * kMaxRanks * 4 <= kPadBytes, "pad too small");
-static_assert(2 * kMaxBlocks * 8 + kFlagOffset <= kSigBytes, "flag region too small");
+static_assert(3 * kMaxBlocks * 8 + kFlagOffset <= 32768, "flag region too small");
 
 int epp_of(int wire) { return wire == F32 ? 4 : 8; }
 
@@ -35,20 +36,15 @@ bool combo_ok(int dtype, int wire) {
     return -1;                                                                             \
   }()
 
-template <typename U, typename W, int OP>
-int launch_direct(int algo, int blocks, cudaStream_t s, const DevComm& dc, const void* in, void* out,
-                  long long n, float scale, int flags, int root) {
-  const U* i = static_cast<const U*>(in);
-  U* o = static_cast<U*>(out);
+template <typename U, typename W, int OP, int NR>
+int launch_direct_nr(int algo, int blocks, cudaStream_t s, const DevComm& dc, const U* i, U* o, long long n,
+                     float scale, int flags, int root) {
   switch (algo) {
     case ONE_SHOT:
-      allreduce_direct_kernel<U, W, OP, ONE_SHOT><<<blocks, kThreads, 0, s>>>(dc, i, o, n, scale, flags, root);
+      allreduce_direct_kernel<U, W, OP, ONE_SHOT, NR><<<blocks, kThreads, 0, s>>>(dc, i, o, n, scale, flags, root);
       break;
     case TWO_SHOT:
-      allreduce_direct_kernel<U, W, OP, TWO_SHOT><<<blocks, kThreads, 0, s>>>(dc, i, o, n, scale, flags, root);
-      break;
-    case NVLS:
-      allreduce_direct_kernel<U, W, OP, NVLS><<<blocks, kThreads, 0, s>>>(dc, i, o, n, scale, flags, root);
+      allreduce_direct_kernel<U, W, OP, TWO_SHOT, NR><<<blocks, kThreads, 0, s>>>(dc, i, o, n, scale, flags, root);
       break;
     default:
       set_error("launch_direct: bad algo %d", algo);
@@ -56,6 +52,23 @@ int launch_direct(int algo, int blocks, cudaStream_t s, const DevComm& dc, const
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+template <typename U, typename W, int OP>
+int launch_direct(int algo, int blocks, cudaStream_t s, const DevComm& dc, const void* in, void* out,
+                  long long n, float scale, int flags, int root) {
+  const U* i = static_cast<const U*>(in);
+  U* o = static_cast<U*>(out);
+  if (algo == NVLS) {
+    allreduce_direct_kernel<U, W, OP, NVLS, 2><<<blocks, kThreads, 0, s>>>(dc, i, o, n, scale, flags, root);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  const int na = dc.n_active;
+  if (na <= 2) return launch_direct_nr<U, W, OP, 2>(algo, blocks, s, dc, i, o, n, scale, flags, root);
+  if (na <= 4) return launch_direct_nr<U, W, OP, 4>(algo, blocks, s, dc, i, o, n, scale, flags, root);
+  if (na <= 8) return launch_direct_nr<U, W, OP, 8>(algo, blocks, s, dc, i, o, n, scale, flags, root);
+  return launch_direct_nr<U, W, OP, 16>(algo, blocks, s, dc, i, o, n, scale, flags, root);
 }
 }  // namespace
 
@@ -161,7 +174,7 @@ int CommContext::pick_algo(int algo, long long wire_bytes, int op, int wire, boo
   if (algo == ONE_SHOT || algo == TWO_SHOT || algo == NVLS) return algo;
   if (algo != AUTO) { set_error("bad algo %d", algo); return -1; }
   if (wire_bytes <= tun.one_shot_max_bytes) return ONE_SHOT;
-  if (nvls_ok && wire_bytes >= tun.nvls_min_bytes) return NVLS;
+  if (nvls_ok && wire_bytes >= tun.nvls_min_bytes && world_ >= tun.nvls_min_ranks) return NVLS;
   return TWO_SHOT;
 }
 
@@ -326,6 +339,9 @@ int CommContext::tree_collective(int prim, const void* in, void* out, long long 
   plan.n_trees = nt;
   plan.do_reduce = prim != BOARDCAST;
   plan.do_bcast = prim != REDUCE;
+  // the API's chunk size is an upper bound; the device pipelines at a finer granularity so
+  // that enough (tree, chunk) items exist to keep every CTA busy
+  if (tun.tree_chunk_max_bytes >= 16 && chunk_bytes > tun.tree_chunk_max_bytes) chunk_bytes = tun.tree_chunk_max_bytes;
   if (chunk_bytes < 16) chunk_bytes = 16;
   plan.chunk_packs = chunk_bytes / 16;
   for (int t = 0; t < nt; ++t) {
@@ -346,8 +362,10 @@ int CommContext::tree_collective(int prim, const void* in, void* out, long long 
     for (int t = 0; t <= nt; ++t) plan.slice_begin[t] = std::min<long long>((long long)t * per, npacks);
     max_chunks = (per + plan.chunk_packs - 1) / plan.chunk_packs;
     const long long items = max_chunks * nt;
-    int blocks = (int)std::min<long long>(items, (long long)std::min(tun.tree_blocks, kMaxBlocks));
-    if (blocks < 1) blocks = 1;
+    // two CTAs per pipeline lane: one on the reduce side, one on the broadcast side
+    int lanes = (int)std::min<long long>(items, (long long)std::min(tun.tree_blocks, kMaxBlocks) / 2);
+    if (lanes < 1) lanes = 1;
+    const int blocks = 2 * lanes;
     const char* pin = (const char*)in + (size_t)done * esize;
     char* pout = (char*)out + (size_t)done * esize;
     int rc = ADAPCC_DISPATCH_TYPES(dtype, wire, {

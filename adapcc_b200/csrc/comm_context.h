@@ -18,9 +18,11 @@ struct Tunables {
   int max_blocks = 64;                 // CTAs per collective kernel (same on all ranks)
   long long one_shot_max_bytes = 256 << 10;   // wire bytes: <= -> one-shot
   long long nvls_min_bytes = 0;        // wire bytes: >= -> NVLS when available
+  int nvls_min_ranks = 3;              // NVLS only pays off when >2 ranks share the switch reduction
   int relay_mode = RELAY_FORWARD;
   long long timeout_ms = 30000;
-  int tree_blocks = 64;
+  int tree_blocks = 128;                // CTAs of the tree kernel (half reduce, half broadcast)
+  long long tree_chunk_max_bytes = 256 << 10;  // device pipelining granularity (wire bytes)
 };
 
 class CommContext {
@@ -64,6 +66,9 @@ class CommContext {
   SymmContext& symm() { return symm_; }
   void* peer_heap_ptr(int r) const { return heap_.peers[r]; }
   void* peer_staging_ptr(int r) const { return staging_.peers[r]; }
+  void* staging_mc_ptr() const { return staging_.mc; }
+  // 2*kMaxRanks u64 ping-pong slots of rank r (inside its signal window)
+  void* profile_flag_ptr(int r) const { return (char*)sig_.peers[r] + 32768; }
 
  private:
   struct Window { char* data[kMaxRanks]; char* mc; size_t capacity; bool zero_copy; };

@@ -38,6 +38,7 @@ enum TreeRoleFlags : int {
   TR_IN_BCAST = 4,      // must pull the result from its parent in the broadcast phase
   TR_WANT_RESULT = 8,   // writes the result into its user tensor
   TR_PUBLISH = 16,      // other ranks pull the result from this rank (has bcast children)
+  TR_PARENT_IS_ROOT = 32,  // my effective parent is the tree's root (selects which flag to wait on)
 };
 
 inline size_t dtype_size(int dt) { return dt == F32 ? 4 : 2; }

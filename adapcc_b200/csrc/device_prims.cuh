@@ -24,8 +24,8 @@ struct DevComm {
   char* data[kMaxRanks];           // data[r]: rank r's symmetric data window, my VA space
   char* mc_data;                   // multicast alias of the same window (or nullptr)
   uint32_t* pad[kMaxRanks];        // pad[r]: rank r's barrier pad  [kMaxBlocks][kMaxRanks]
-  unsigned long long* flag[kMaxRanks];  // flag[r]: rank r's chunk flags [2][kMaxBlocks]
-  uint32_t* bar_epoch;             // local, [kMaxBlocks]: barrier epoch per block
+  unsigned long long* flag[kMaxRanks];  // flag[r]: rank r's chunk flags [3][kMaxBlocks]
+  uint32_t* bar_epoch;             // local, [kMaxBlocks][kMaxRanks]: barrier epoch per (block, peer)
   unsigned long long* seq;         // local: op sequence number of this context
   uint32_t* ticket;                // local: last-block ticket
   uint32_t* err;                   // local: sticky error word (timeouts)
@@ -88,24 +88,40 @@ __device__ __forceinline__ bool wait_flag64(const DevComm& c, const unsigned lon
 // through the phases of a collective (no grid-wide sync). The release/acquire pair makes
 // every write the block did before the barrier (local, peer or multicast) visible to the
 // peers' block b after it.
-__device__ __forceinline__ void block_barrier(const DevComm& c, uint32_t& epoch) {
+//
+// Epochs are kept PER PAIR (block, peer): with relay control different ranks execute
+// different numbers of barriers (a rank skips the ops it is not active in), but any barrier
+// that involves both r and p is executed by both, so the pairwise counters stay equal.
+// Thread t < n_active owns the pair (this rank, active_ranks[t]) for the whole kernel.
+struct BarrierState {
+  uint32_t epoch;    // value of the last barrier with my peer (threads >= n_active: unused)
+  int peer;
+};
+
+__device__ __forceinline__ BarrierState barrier_begin(const DevComm& c) {
+  BarrierState b;
+  b.peer = (int)threadIdx.x < c.n_active ? c.active_ranks[threadIdx.x] : -1;
+  b.epoch = b.peer >= 0 ? c.bar_epoch[blockIdx.x * kMaxRanks + b.peer] : 0u;
+  return b;
+}
+
+__device__ __forceinline__ void block_barrier(const DevComm& c, BarrierState& b) {
   __syncthreads();
-  epoch += 1;
-  if ((int)threadIdx.x < c.n_active) {
-    const int peer = c.active_ranks[threadIdx.x];
-    st_release_sys(c.pad[peer] + blockIdx.x * kMaxRanks + c.rank, epoch);
-    wait_flag32(c, c.pad[c.rank] + blockIdx.x * kMaxRanks + peer, epoch);
+  if (b.peer >= 0) {
+    b.epoch += 1;
+    st_release_sys(c.pad[b.peer] + blockIdx.x * kMaxRanks + c.rank, b.epoch);
+    wait_flag32(c, c.pad[c.rank] + blockIdx.x * kMaxRanks + b.peer, b.epoch);
   }
   __syncthreads();
 }
 
-// Every kernel ends with this: persist the block's barrier epoch and let the last block
-// to finish advance the context's op sequence number (device-side, so the kernels stay
-// CUDA-graph capturable: no host-computed epoch is baked into the launch).
-__device__ __forceinline__ void finish_op(const DevComm& c, uint32_t epoch) {
+// Every kernel ends with this: persist the pair epochs and let the last block to finish
+// advance the context's op sequence number (device-side, so the kernels stay CUDA-graph
+// capturable: no host-computed epoch is baked into the launch).
+__device__ __forceinline__ void finish_op(const DevComm& c, const BarrierState& b) {
+  if (b.peer >= 0) c.bar_epoch[blockIdx.x * kMaxRanks + b.peer] = b.epoch;
   __syncthreads();
   if (threadIdx.x == 0) {
-    c.bar_epoch[blockIdx.x] = epoch;
     __threadfence();
     const uint32_t t = atomicAdd(c.ticket, 1u);
     if (t == gridDim.x - 1) {

@@ -88,14 +88,154 @@ __device__ __forceinline__ void stage_out(const Partition& P, U* __restrict__ ou
 }
 
 // ----------------------------------------------------------------------------------
+// phase-1 bodies, specialised on NR = upper bound of participants (2/4/8/16) so that
+// NR x UN = 16 independent 128-bit peer loads are in flight per thread: NVLink round trips
+// are ~2 us, bandwidth comes from bytes in flight, not from thread count.
+// ----------------------------------------------------------------------------------
+template <typename U, typename W, int OP, int NR>
+__device__ __forceinline__ void one_shot_phase1(const DevComm& c, long long npacks, U* __restrict__ out,
+                                                long long n, bool out_vec, float scale) {
+  constexpr int kEpp = WireTraits<W>::kEpp;
+  constexpr int UN = 16 / NR;
+  const int na = c.n_active;
+  const long long stride = (long long)gridDim.x * kThreads;
+  const char* peers[NR];
+#pragma unroll
+  for (int a = 0; a < NR; ++a) peers[a] = a < na ? c.data[c.active_ranks[a]] : nullptr;
+  for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < npacks; j0 += stride * UN) {
+    uint4 v[UN][NR];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long j = j0 + u * stride;
+      if (j < npacks) {
+#pragma unroll
+        for (int a = 0; a < NR; ++a)
+          if (a < na) v[u][a] = ld16(peers[a] + j * 16);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long j = j0 + u * stride;
+      if (j < npacks) {
+        float acc[kEpp];
+#pragma unroll
+        for (int i = 0; i < kEpp; ++i) acc[i] = red_identity<OP>();
+#pragma unroll
+        for (int a = 0; a < NR; ++a)   // fixed rank order: bit-identical on every replica
+          if (a < na) {
+            float f[kEpp];
+            unpack<W>(v[u][a], f);
+#pragma unroll
+            for (int i = 0; i < kEpp; ++i) acc[i] = red_apply<OP>(acc[i], f[i]);
+          }
+#pragma unroll
+        for (int i = 0; i < kEpp; ++i) acc[i] *= scale;
+        store_user<U, kEpp>(out, j * kEpp, n, out_vec, acc);
+      }
+    }
+  }
+}
+
+template <typename W, int OP, int NR>
+__device__ __forceinline__ void two_shot_phase1(const DevComm& c, long long base, long long cnt,
+                                                bool zero_copy, float scale, bool root_only, int root) {
+  constexpr int kEpp = WireTraits<W>::kEpp;
+  constexpr int UN = 16 / NR;
+  const int na = c.n_active, me = c.my_index;
+  const long long stride = (long long)gridDim.x * kThreads;
+  char* peers[NR];
+#pragma unroll
+  for (int a = 0; a < NR; ++a) {
+    int idx = me + a;                       // stagger: rank r starts with its own window
+    if (idx >= na) idx -= na;
+    peers[a] = a < na ? c.data[c.active_ranks[idx]] : nullptr;
+  }
+  char* const root_ptr = root_only ? c.data[c.active_ranks[root]] : nullptr;
+  for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < cnt; j0 += stride * UN) {
+    uint4 v[UN][NR];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long j = j0 + u * stride;
+      if (j < cnt) {
+#pragma unroll
+        for (int a = 0; a < NR; ++a)
+          if (a < na) v[u][a] = ld16(peers[a] + (base + j) * 16);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long j = j0 + u * stride;
+      if (j < cnt) {
+        const long long off = (base + j) * 16;
+        float acc[kEpp];
+#pragma unroll
+        for (int i = 0; i < kEpp; ++i) acc[i] = red_identity<OP>();
+#pragma unroll
+        for (int a = 0; a < NR; ++a)
+          if (a < na) {
+            float f[kEpp];
+            unpack<W>(v[u][a], f);
+#pragma unroll
+            for (int i = 0; i < kEpp; ++i) acc[i] = red_apply<OP>(acc[i], f[i]);
+          }
+        if (zero_copy) {
+#pragma unroll
+          for (int i = 0; i < kEpp; ++i) acc[i] *= scale;
+        }
+        const uint4 r = pack<W>(acc);
+        if (root_only) {
+          st16(root_ptr + off, r);
+        } else {
+#pragma unroll
+          for (int a = 0; a < NR; ++a)
+            if (a < na) st16(peers[a] + off, r);
+        }
+      }
+    }
+  }
+}
+
+template <typename W, int OP>
+__device__ __forceinline__ void nvls_phase1(const DevComm& c, long long base, long long cnt, bool zero_copy,
+                                            float scale, bool root_only, int root) {
+  constexpr int kEpp = WireTraits<W>::kEpp;
+  constexpr int UN = 8;
+  const long long stride = (long long)gridDim.x * kThreads;
+  char* const root_ptr = root_only ? c.data[c.active_ranks[root]] : nullptr;
+  for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < cnt; j0 += stride * UN) {
+    uint4 v[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long j = j0 + u * stride;
+      if (j < cnt) v[u] = mc_ld_reduce<W, OP>(c.mc_data + (base + j) * 16);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long j = j0 + u * stride;
+      if (j < cnt) {
+        if (zero_copy && scale != 1.f) {
+          float f[kEpp];
+          unpack<W>(v[u], f);
+#pragma unroll
+          for (int i = 0; i < kEpp; ++i) f[i] *= scale;
+          v[u] = pack<W>(f);
+        }
+        if (root_only) st16(root_ptr + (base + j) * 16, v[u]);
+        else mc_st16(c.mc_data + (base + j) * 16, v[u]);
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------
 // all-reduce / reduce, direct algorithms
 // ----------------------------------------------------------------------------------
-template <typename U, typename W, int OP, int ALGO>
+template <typename U, typename W, int OP, int ALGO, int NR>
 __global__ void __launch_bounds__(kThreads, 1)
 allreduce_direct_kernel(const __grid_constant__ DevComm c, const U* __restrict__ in, U* __restrict__ out,
                         long long n, float scale, int flags, int root) {
   constexpr int kEpp = WireTraits<W>::kEpp;
-  uint32_t epoch = c.bar_epoch[blockIdx.x];
+  BarrierState epoch = barrier_begin(c);
   const int na = c.n_active, me = c.my_index;
   const bool zero_copy = flags & F_ZERO_COPY;
   const bool root_only = flags & F_ROOT_ONLY;
@@ -107,7 +247,6 @@ allreduce_direct_kernel(const __grid_constant__ DevComm c, const U* __restrict__
   P.npacks = (n + kEpp - 1) / kEpp;
   P.nslices = (ALGO == ONE_SHOT) ? 1 : na;
   P.pps = (P.npacks + P.nslices - 1) / P.nslices;
-  const long long stride = (long long)gridDim.x * kThreads;
 
   // ---- phase 0: publish my contribution -------------------------------------------
   if (!zero_copy) stage_in<U, W>(P, in, n, in_vec, local);
@@ -115,96 +254,15 @@ allreduce_direct_kernel(const __grid_constant__ DevComm c, const U* __restrict__
 
   // ---- phase 1: reduce (+ redistribute) -------------------------------------------
   if (ALGO == ONE_SHOT) {
-    // every rank pulls every peer's window and reduces locally, fixed rank order so all
-    // replicas get bit-identical sums. Result goes straight to the user tensor.
-    if (!root_only || me == root) {
-      for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < P.npacks; j0 += stride) {
-        uint4 v[kMaxRanks];
-#pragma unroll
-        for (int a = 0; a < kMaxRanks; ++a)
-          if (a < na) v[a] = ld16(c.data[c.active_ranks[a]] + j0 * 16);
-        float acc[kEpp];
-#pragma unroll
-        for (int i = 0; i < kEpp; ++i) acc[i] = red_identity<OP>();
-#pragma unroll
-        for (int a = 0; a < kMaxRanks; ++a)
-          if (a < na) {
-            float f[kEpp];
-            unpack<W>(v[a], f);
-#pragma unroll
-            for (int i = 0; i < kEpp; ++i) acc[i] = red_apply<OP>(acc[i], f[i]);
-          }
-#pragma unroll
-        for (int i = 0; i < kEpp; ++i) acc[i] *= scale;
-        store_user<U, kEpp>(out, j0 * kEpp, n, out_vec, acc);
-      }
-    }
+    // every rank pulls every peer's window and reduces locally; the result goes straight
+    // to the user tensor (no stage-out pass).
+    if (!root_only || me == root) one_shot_phase1<U, W, OP, NR>(c, P.npacks, out, n, out_vec, scale);
     // peers may still be reading my window: nobody leaves before everyone is done
     block_barrier(c, epoch);
   } else {
     const long long base = P.slice_begin(me), cnt = P.slice_count(me);
-    if (ALGO == TWO_SHOT) {
-      for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < cnt; j0 += stride) {
-        const long long off = (base + j0) * 16;
-        uint4 v[kMaxRanks];
-#pragma unroll
-        for (int a = 0; a < kMaxRanks; ++a)
-          if (a < na) {
-            int idx = me + a; if (idx >= na) idx -= na;       // stagger peers
-            v[a] = ld16(c.data[c.active_ranks[idx]] + off);
-          }
-        float acc[kEpp];
-#pragma unroll
-        for (int i = 0; i < kEpp; ++i) acc[i] = red_identity<OP>();
-#pragma unroll
-        for (int a = 0; a < kMaxRanks; ++a)
-          if (a < na) {
-            float f[kEpp];
-            unpack<W>(v[a], f);
-#pragma unroll
-            for (int i = 0; i < kEpp; ++i) acc[i] = red_apply<OP>(acc[i], f[i]);
-          }
-        if (zero_copy) {
-#pragma unroll
-          for (int i = 0; i < kEpp; ++i) acc[i] *= scale;
-        }
-        const uint4 r = pack<W>(acc);
-        if (root_only) {
-          st16(c.data[c.active_ranks[root]] + off, r);
-        } else {
-#pragma unroll
-          for (int a = 0; a < kMaxRanks; ++a)
-            if (a < na) {
-              int idx = me + a; if (idx >= na) idx -= na;
-              st16(c.data[c.active_ranks[idx]] + off, r);
-            }
-        }
-      }
-    } else {  // NVLS: the switch reduces on the way in and replicates on the way out
-      for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < cnt; j0 += stride * kUnroll) {
-        uint4 v[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const long long j = j0 + u * stride;
-          if (j < cnt) v[u] = mc_ld_reduce<W, OP>(c.mc_data + (base + j) * 16);
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const long long j = j0 + u * stride;
-          if (j < cnt) {
-            if (zero_copy && scale != 1.f) {
-              float f[kEpp];
-              unpack<W>(v[u], f);
-#pragma unroll
-              for (int i = 0; i < kEpp; ++i) f[i] *= scale;
-              v[u] = pack<W>(f);
-            }
-            if (root_only) st16(c.data[c.active_ranks[root]] + (base + j) * 16, v[u]);
-            else mc_st16(c.mc_data + (base + j) * 16, v[u]);
-          }
-        }
-      }
-    }
+    if (ALGO == TWO_SHOT) two_shot_phase1<W, OP, NR>(c, base, cnt, zero_copy, scale, root_only, root);
+    else nvls_phase1<W, OP>(c, base, cnt, zero_copy, scale, root_only, root);
     block_barrier(c, epoch);
     // ---- phase 2: hand the result back to the caller ------------------------------
     if (!zero_copy && (!root_only || me == root))
@@ -221,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 broadcast_direct_kernel(const __grid_constant__ DevComm c, U* __restrict__ buf, long long n, int root,
                         int use_mc, int flags) {
   constexpr int kEpp = WireTraits<W>::kEpp;
-  uint32_t epoch = c.bar_epoch[blockIdx.x];
+  BarrierState epoch = barrier_begin(c);
   const int na = c.n_active, me = c.my_index;
   const bool zero_copy = flags & F_ZERO_COPY;
   const bool vec = (reinterpret_cast<uintptr_t>(buf) & 15) == 0;

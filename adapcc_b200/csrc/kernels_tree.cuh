@@ -33,18 +33,97 @@ struct TreePlan {
   TreeRole role[kMaxTrees];
 };
 
+// One chunk of the reduce phase: acc = (own data) (+) children's partial sums. Children are
+// pulled NCB at a time with UN packs each, i.e. NCB x UN independent 128-bit peer loads in
+// flight per thread on top of the UN local loads.
+template <typename U, typename W, int OP, int NCB, int UN>
+__device__ __forceinline__ void reduce_chunk(const DevComm& c, const TreeRole& role, long long p0, long long pc,
+                                             const U* __restrict__ in, U* __restrict__ out, long long n,
+                                             bool in_vec, bool out_vec, char* __restrict__ local, bool has_local,
+                                             bool is_root, bool to_window, bool to_user, float scale) {
+  constexpr int kEpp = WireTraits<W>::kEpp;
+  const int nc = role.n_children;
+  for (long long j0 = threadIdx.x; j0 < pc; j0 += (long long)kThreads * UN) {
+    float acc[UN][kEpp];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long j = j0 + (long long)u * kThreads;
+      if (j < pc && has_local) {
+        load_user<U, kEpp>(in, (p0 + j) * kEpp, n, in_vec, acc[u]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kEpp; ++i) acc[u][i] = red_identity<OP>();
+      }
+    }
+    for (int a0 = 0; a0 < nc; a0 += NCB) {
+      uint4 v[UN][NCB];
+#pragma unroll
+      for (int b = 0; b < NCB; ++b) {
+        if (a0 + b < nc) {
+          const char* kid = c.data[role.children[a0 + b]];
+#pragma unroll
+          for (int u = 0; u < UN; ++u) {
+            const long long j = j0 + (long long)u * kThreads;
+            if (j < pc) v[u][b] = ld16(kid + (p0 + j) * 16);
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < NCB; ++b) {
+        if (a0 + b < nc) {
+#pragma unroll
+          for (int u = 0; u < UN; ++u) {
+            const long long j = j0 + (long long)u * kThreads;
+            if (j < pc) {
+              float f[kEpp];
+              unpack<W>(v[u][b], f);
+#pragma unroll
+              for (int i = 0; i < kEpp; ++i) acc[u][i] = red_apply<OP>(acc[u][i], f[i]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long j = j0 + (long long)u * kThreads;
+      if (j < pc) {
+        if (is_root) {
+#pragma unroll
+          for (int i = 0; i < kEpp; ++i) acc[u][i] *= scale;
+        }
+        if (to_window) st16(local + (p0 + j) * 16, pack<W>(acc[u]));
+        if (to_user) store_user<U, kEpp>(out, (p0 + j) * kEpp, n, out_vec, acc[u]);
+      }
+    }
+  }
+}
+
+// The grid is split in two halves, like the reference's reduce thread + broadcast thread per
+// tree (/root/reference/csrc/allreduce.cu:735-742): CTAs [0, G/2) run the reduce pipeline over
+// the (tree, chunk) items, CTAs [G/2, G) run the broadcast pipeline over the same items. The
+// root's reduce CTA b hands chunk after chunk to the broadcast side through bflag[b] — the
+// device-side equivalent of the reference's bcstCount mailbox (allreduce.cu:651-653) — so a
+// chunk travels down while later chunks are still being reduced and neither pipeline ever
+// idles waiting for the other phase.
 template <typename U, typename W, int OP>
 __global__ void __launch_bounds__(kThreads, 1)
 tree_collective_kernel(const __grid_constant__ DevComm c, const __grid_constant__ TreePlan plan,
                        const U* __restrict__ in, U* __restrict__ out, long long n, float scale) {
   constexpr int kEpp = WireTraits<W>::kEpp;
-  uint32_t epoch = c.bar_epoch[blockIdx.x];
+  BarrierState epoch = barrier_begin(c);
   const unsigned long long q = *c.seq;
   const bool in_vec = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
   const bool out_vec = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   char* const local = c.data[c.rank];
-  unsigned long long* const my_rflag = c.flag[c.rank] + blockIdx.x;
-  unsigned long long* const my_bflag = c.flag[c.rank] + kMaxBlocks + blockIdx.x;
+  const int half = gridDim.x >> 1;
+  const bool bcast_side = (int)blockIdx.x >= half;
+  const int lane = bcast_side ? blockIdx.x - half : blockIdx.x;   // pipeline lane 0..half-1
+  unsigned long long* const my_rflag = c.flag[c.rank] + lane;
+  // three single-writer flag words per lane: partial sum ready (reduce CTA), result ready at
+  // the root (root's reduce CTA), result forwarded (broadcast CTA)
+  unsigned long long* const my_root_bflag = c.flag[c.rank] + kMaxBlocks + lane;
+  unsigned long long* const my_fwd_bflag = c.flag[c.rank] + 2 * kMaxBlocks + lane;
 
   long long max_k = 0;
   for (int t = 0; t < plan.n_trees; ++t) {
@@ -55,7 +134,7 @@ tree_collective_kernel(const __grid_constant__ DevComm c, const __grid_constant_
   const long long n_items = max_k * plan.n_trees;
 
   unsigned long long m = 0;
-  for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++m) {
+  for (long long item = lane; item < n_items; item += half, ++m) {
     const int t = (int)(item % plan.n_trees);
     const long long k = item / plan.n_trees;
     const long long p0 = plan.slice_begin[t] + k * plan.chunk_packs;
@@ -67,86 +146,72 @@ tree_collective_kernel(const __grid_constant__ DevComm c, const __grid_constant_
     const bool is_root = role.parent < 0;
     const int nc = role.n_children;
 
-    // ------------------------------ reduce phase ---------------------------------
-    if (plan.do_reduce && (role.flags & TR_IN_REDUCE)) {
-      if (nc > 0) {
-        if ((int)threadIdx.x < nc) wait_flag64(c, c.flag[role.children[threadIdx.x]] + blockIdx.x, token);
+    if (!bcast_side) {
+      // ------------------------------ reduce pipeline ------------------------------
+      if (plan.do_reduce && (role.flags & TR_IN_REDUCE)) {
+        if (nc > 0) {
+          if ((int)threadIdx.x < nc) wait_flag64(c, c.flag[role.children[threadIdx.x]] + lane, token);
+          __syncthreads();
+        }
+        const bool has_local = role.flags & TR_HAS_LOCAL;
+        const bool to_user = is_root && (role.flags & TR_WANT_RESULT);
+        const bool to_window = !is_root || (plan.do_bcast && (role.flags & TR_PUBLISH));
+        reduce_chunk<U, W, OP, 2, 4>(c, role, p0, pc, in, out, n, in_vec, out_vec, local, has_local, is_root,
+                                     to_window, to_user, scale);
         __syncthreads();
-      }
-      const bool has_local = role.flags & TR_HAS_LOCAL;
-      const bool to_user = is_root && (role.flags & TR_WANT_RESULT);
-      const bool to_window = !is_root || (plan.do_bcast && (role.flags & TR_PUBLISH));
-      for (long long j = threadIdx.x; j < pc; j += kThreads) {
-        const long long pk = p0 + j;
-        uint4 v[kMaxChildren];
+        if (threadIdx.x == 0) st_release_sys64(is_root ? my_root_bflag : my_rflag, token);
+      } else if (!plan.do_reduce && plan.do_bcast && is_root) {
+        // pure broadcast: the root publishes its tensor chunk by chunk
+        for (long long j0 = threadIdx.x; j0 < pc; j0 += (long long)kThreads * kUnroll) {
+          float f[kUnroll][kEpp];
 #pragma unroll
-        for (int a = 0; a < kMaxChildren; ++a)
-          if (a < nc) v[a] = ld16(c.data[role.children[a]] + pk * 16);
-        float acc[kEpp];
-        if (has_local) {
-          load_user<U, kEpp>(in, pk * kEpp, n, in_vec, acc);
-        } else {
-#pragma unroll
-          for (int i = 0; i < kEpp; ++i) acc[i] = red_identity<OP>();
-        }
-#pragma unroll
-        for (int a = 0; a < kMaxChildren; ++a)
-          if (a < nc) {
-            float f[kEpp];
-            unpack<W>(v[a], f);
-#pragma unroll
-            for (int i = 0; i < kEpp; ++i) acc[i] = red_apply<OP>(acc[i], f[i]);
+          for (int u = 0; u < kUnroll; ++u) {
+            const long long j = j0 + (long long)u * kThreads;
+            if (j < pc) load_user<U, kEpp>(in, (p0 + j) * kEpp, n, in_vec, f[u]);
           }
-        if (is_root) {
 #pragma unroll
-          for (int i = 0; i < kEpp; ++i) acc[i] *= scale;
+          for (int u = 0; u < kUnroll; ++u) {
+            const long long j = j0 + (long long)u * kThreads;
+            if (j < pc) st16(local + (p0 + j) * 16, pack<W>(f[u]));
+          }
         }
-        if (to_window) st16(local + pk * 16, pack<W>(acc));
-        if (to_user) store_user<U, kEpp>(out, pk * kEpp, n, out_vec, acc);
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_sys64(my_root_bflag, token);
       }
-      __syncthreads();
-      if (threadIdx.x == 0) st_release_sys64(is_root ? my_bflag : my_rflag, token);
-    } else if (!plan.do_reduce && plan.do_bcast && is_root) {
-      // pure broadcast: the root publishes its tensor chunk by chunk
-      for (long long j = threadIdx.x; j < pc; j += kThreads) {
-        float f[kEpp];
-        load_user<U, kEpp>(in, (p0 + j) * kEpp, n, in_vec, f);
-        st16(local + (p0 + j) * 16, pack<W>(f));
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) st_release_sys64(my_bflag, token);
-    }
-
-    // ----------------------------- broadcast phase -------------------------------
-    if (plan.do_bcast && !is_root && (role.flags & TR_IN_BCAST)) {
-      if (threadIdx.x == 0) wait_flag64(c, c.flag[role.parent] + kMaxBlocks + blockIdx.x, token);
-      __syncthreads();
-      const bool publish = role.flags & TR_PUBLISH;
-      const bool want = role.flags & TR_WANT_RESULT;
-      const char* src = c.data[role.parent];
-      for (long long j0 = threadIdx.x; j0 < pc; j0 += kThreads * kUnroll) {
-        uint4 v[kUnroll];
+    } else {
+      // ----------------------------- broadcast pipeline ----------------------------
+      if (plan.do_bcast && !is_root && (role.flags & TR_IN_BCAST)) {
+        if (threadIdx.x == 0)
+          wait_flag64(c, c.flag[role.parent] + ((role.flags & TR_PARENT_IS_ROOT) ? 1 : 2) * kMaxBlocks + lane, token);
+        __syncthreads();
+        const bool publish = role.flags & TR_PUBLISH;
+        const bool want = role.flags & TR_WANT_RESULT;
+        const char* src = c.data[role.parent];
+        constexpr int UB = 8;
+        for (long long j0 = threadIdx.x; j0 < pc; j0 += (long long)kThreads * UB) {
+          uint4 v[UB];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const long long j = j0 + (long long)u * kThreads;
-          if (j < pc) v[u] = ld16(src + (p0 + j) * 16);
-        }
+          for (int u = 0; u < UB; ++u) {
+            const long long j = j0 + (long long)u * kThreads;
+            if (j < pc) v[u] = ld16(src + (p0 + j) * 16);
+          }
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const long long j = j0 + (long long)u * kThreads;
-          if (j < pc) {
-            if (publish) st16(local + (p0 + j) * 16, v[u]);
-            if (want) {
-              float f[kEpp];
-              unpack<W>(v[u], f);
-              store_user<U, kEpp>(out, (p0 + j) * kEpp, n, out_vec, f);
+          for (int u = 0; u < UB; ++u) {
+            const long long j = j0 + (long long)u * kThreads;
+            if (j < pc) {
+              if (publish) st16(local + (p0 + j) * 16, v[u]);
+              if (want) {
+                float f[kEpp];
+                unpack<W>(v[u], f);
+                store_user<U, kEpp>(out, (p0 + j) * kEpp, n, out_vec, f);
+              }
             }
           }
         }
-      }
-      if (publish) {
-        __syncthreads();
-        if (threadIdx.x == 0) st_release_sys64(my_bflag, token);
+        if (publish) {
+          __syncthreads();
+          if (threadIdx.x == 0) st_release_sys64(my_fwd_bflag, token);
+        }
       }
     }
   }

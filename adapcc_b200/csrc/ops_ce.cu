@@ -1,0 +1,103 @@
+// Fused softmax cross-entropy (forward + backward, in place) for the chunked LM head of the
+// GPT-2 workload (adapcc_b200/models/gpt2.py).
+//
+// One CTA per row of bf16 logits [rows, stride] (stride = vocab padded to a multiple of 8 so every
+// row is 16-byte aligned): pass 1 computes the online max / sum-exp with 128-bit loads, pass 2
+// re-reads the row (L2 resident: a row is ~100 KB) and overwrites it with
+// d loss / d logits = (softmax - onehot) * valid, also in bf16. Per-row losses go to a float
+// array. Columns >= vocab are padding: they read as -inf and get zero gradient. Compared with the
+// eager chain (float cast, logsumexp, softmax, scatter, mask, cast back: ~17 bytes/logit of HBM
+// traffic) this moves 4 bytes/logit.
+#include <cuda_bf16.h>
+
+#include "common.h"
+
+namespace adapcc {
+
+__device__ __forceinline__ void online_combine(float& m, float& s, float m2, float s2) {
+  const float mx = fmaxf(m, m2);
+  s = s * __expf(m - mx) + s2 * __expf(m2 - mx);
+  m = mx;
+}
+
+__global__ void __launch_bounds__(512)
+fused_ce_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restrict__ labels,
+                float* __restrict__ row_loss, int vocab, int stride) {
+  const int row = blockIdx.x;
+  __nv_bfloat16* p = logits + (long long)row * stride;
+  const long long label = labels[row];
+  const bool valid = label >= 0 && label < vocab;
+  const int nvec = stride / 8;
+
+  float m = -INFINITY, s = 0.f;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    uint4 q = reinterpret_cast<const uint4*>(p)[v];
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      x[2 * i] = __uint_as_float(w[i] << 16);
+      x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+    float lm = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (v * 8 + i >= vocab) x[i] = -INFINITY;
+      lm = fmaxf(lm, x[i]);
+    }
+    if (lm > -INFINITY) {
+      float ls = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ls += __expf(x[i] - lm);
+      online_combine(m, s, lm, ls);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    if (m2 > -INFINITY || m > -INFINITY) online_combine(m, s, m2, s2);
+  }
+  __shared__ float sm[16], ss[16];
+  if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = m; ss[threadIdx.x >> 5] = s; }
+  __syncthreads();
+  m = sm[0]; s = ss[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+    if (sm[w] > -INFINITY || m > -INFINITY) online_combine(m, s, sm[w], ss[w]);
+  const float inv = 1.f / s;
+  if (threadIdx.x == 0) {
+    const float xl = valid ? __bfloat162float(p[label]) : 0.f;
+    row_loss[row] = valid ? (__logf(s) + m - xl) : 0.f;
+  }
+  __syncthreads();   // the label logit above must be read before the row is overwritten
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    uint4 q = reinterpret_cast<const uint4*>(p)[v];
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = __uint_as_float(w[i] << 16), b = __uint_as_float(w[i] & 0xffff0000u);
+      const int c = v * 8 + 2 * i;
+      float ga = (valid && c < vocab) ? __expf(a - m) * inv - (c == label ? 1.f : 0.f) : 0.f;
+      float gb = (valid && c + 1 < vocab) ? __expf(b - m) * inv - (c + 1 == label ? 1.f : 0.f) : 0.f;
+      __nv_bfloat162 r = __floats2bfloat162_rn(ga, gb);
+      o[i] = *reinterpret_cast<uint32_t*>(&r);
+    }
+    reinterpret_cast<uint4*>(p)[v] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+}  // namespace adapcc
+
+extern "C" int adapcc_fused_ce(void* logits, const long long* labels, float* row_loss, int rows, int vocab,
+                               int stride, void* stream) {
+  using namespace adapcc;
+  if (rows <= 0) return 0;
+  if (stride % 8 != 0 || (reinterpret_cast<uintptr_t>(logits) & 15)) {
+    set_error("fused_ce: stride must be a multiple of 8 and logits 16-byte aligned");
+    return -1;
+  }
+  if (vocab > stride) { set_error("fused_ce: vocab > stride"); return -1; }
+  fused_ce_kernel<<<rows, 512, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)logits, labels, row_loss, vocab, stride);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}

@@ -234,6 +234,7 @@ HostTreeRole tree_role(const StrategyTree& tree_in, int rank, const std::vector<
       if (subtree_active(*T, c, active)) recvs.push_back(c);
   auto pit = T->parent.find(rank);
   role.parent = is_root ? -1 : (pit == T->parent.end() ? -1 : pit->second);
+  const int parent_is_root = (role.parent >= 0 && role.parent == T->root) ? TR_PARENT_IS_ROOT : 0;
 
   if (prim == ALLREDUCE || prim == REDUCE) {
     const bool in_reduce = local || !recvs.empty();
@@ -242,7 +243,7 @@ HostTreeRole tree_role(const StrategyTree& tree_in, int rank, const std::vector<
     if (local) role.flags |= TR_HAS_LOCAL;
     role.children = recvs;
     if (prim == ALLREDUCE) {
-      if (!is_root) role.flags |= TR_IN_BCAST;
+      if (!is_root) role.flags |= TR_IN_BCAST | parent_is_root;
       if (local) role.flags |= TR_WANT_RESULT;
       if (!recvs.empty()) role.flags |= TR_PUBLISH;
     } else if (is_root) {
@@ -254,7 +255,7 @@ HostTreeRole tree_role(const StrategyTree& tree_in, int rank, const std::vector<
       role.flags |= TR_PUBLISH;            // owns the data (never overwritten)
     } else {
       if (!local && !wants_below) { role.parent = -1; return role; }
-      role.flags |= TR_IN_BCAST;
+      role.flags |= TR_IN_BCAST | parent_is_root;
       if (local) role.flags |= TR_WANT_RESULT;
       if (wants_below) role.flags |= TR_PUBLISH;
     }

@@ -1,0 +1,191 @@
+"""GPT-2 small with the "double heads" (LM + multiple choice) of the reference's flagship workload.
+
+The reference trains ``transformers.GPT2DoubleHeadsModel(GPT2Config())`` (12 layers, d=768, 12 heads,
+ctx 1024, vocab 50257 + 5 special tokens) on PersonaChat-shaped batches
+``input_ids/token_type_ids/lm_labels [B, C, T]``, ``mc_token_ids [B, C]``, ``mc_labels [B]`` with
+loss = lm_coef * LM cross-entropy + mc_coef * multiple-choice cross-entropy
+(/root/reference/models/gpt2/train_gpt2_ddp.py:28-31,100-107,157-195). This is the same
+architecture written for B200 training:
+
+* parameters live in bf16 (fp32 master copy inside the fused optimizer), so gradients are born in
+  bf16 and the gradient all-reduce moves half the bytes with fp32 accumulation in the kernel;
+* attention goes through ``scaled_dot_product_attention`` (flash kernels), MLP through cuBLAS;
+* the LM head + cross-entropy is evaluated in row chunks so the [tokens, vocab] logits are never
+  materialised at once (50 262 x 8192 x 4 B = 1.6 GB otherwise);
+* no data-dependent host syncs: the whole step can be captured in one CUDA graph.
+
+Token-type embeddings reuse ``wte`` exactly as HF GPT-2 does.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+@dataclass
+class GPT2Config:
+    vocab_size: int = 50257 + 5          # GPT2Config() + the five PersonaChat special tokens
+    n_positions: int = 1024
+    n_embd: int = 768
+    n_layer: int = 12
+    n_head: int = 12
+    layer_norm_epsilon: float = 1e-5
+    initializer_range: float = 0.02
+    lm_chunk_rows: int = 2048            # rows of the fused LM-head/CE evaluated at a time
+
+    @classmethod
+    def tiny(cls) -> "GPT2Config":
+        return cls(vocab_size=512, n_positions=64, n_embd=64, n_layer=2, n_head=4, lm_chunk_rows=64)
+
+
+class Block(nn.Module):
+    def __init__(self, cfg: GPT2Config):
+        super().__init__()
+        d = cfg.n_embd
+        self.n_head = cfg.n_head
+        self.ln_1 = nn.LayerNorm(d, eps=cfg.layer_norm_epsilon)
+        self.c_attn = nn.Linear(d, 3 * d)
+        self.c_proj = nn.Linear(d, d)
+        self.ln_2 = nn.LayerNorm(d, eps=cfg.layer_norm_epsilon)
+        self.c_fc = nn.Linear(d, 4 * d)
+        self.c_proj2 = nn.Linear(4 * d, d)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        B, T, D = x.shape
+        h = self.ln_1(x)
+        q, k, v = self.c_attn(h).view(B, T, 3, self.n_head, D // self.n_head).permute(2, 0, 3, 1, 4)
+        a = F.scaled_dot_product_attention(q, k, v, is_causal=True)
+        x = x + self.c_proj(a.transpose(1, 2).reshape(B, T, D))
+        h = self.ln_2(x)
+        x = x + self.c_proj2(F.gelu(self.c_fc(h), approximate="tanh"))
+        return x
+
+
+class _ChunkedLMLoss(torch.autograd.Function):
+    """sum over rows of CE(h @ W^T, labels), ``chunk`` rows at a time. The backward of every chunk
+    is produced inside the forward pass (fused softmax-CE kernel overwrites the bf16 logits with
+    their gradient), so logits never outlive a chunk and are touched twice instead of ~8 times."""
+
+    @staticmethod
+    def forward(ctx, h, weight, labels, chunk, vocab):
+        n = h.shape[0]
+        use_kernel = h.is_cuda and h.dtype == torch.bfloat16 and weight.shape[0] % 8 == 0
+        grad_h = torch.empty_like(h)
+        grad_w = torch.zeros(weight.shape, dtype=torch.float32, device=h.device)
+        total = torch.zeros((), dtype=torch.float32, device=h.device)
+        if use_kernel:
+            from ..ops import fused_ce_
+        for s in range(0, n, chunk):
+            hs = h[s:s + chunk]
+            ls = labels[s:s + chunk]
+            logits = hs @ weight.t()
+            if use_kernel:
+                total += fused_ce_(logits, ls, vocab).sum()
+                g = logits                                         # now d loss / d logits (bf16)
+            else:                                                  # CPU / fp32 reference path
+                lf = logits.float()
+                lf[:, vocab:] = float("-inf")
+                valid = (ls >= 0)
+                lse = torch.logsumexp(lf, dim=-1)
+                tgt = lf.gather(1, ls.clamp(min=0).unsqueeze(1)).squeeze(1)
+                total += ((lse - tgt) * valid).sum()
+                p = torch.softmax(lf, dim=-1)
+                p.scatter_add_(1, ls.clamp(min=0).unsqueeze(1), -torch.ones_like(p[:, :1]))
+                g = (p * valid.unsqueeze(1)).to(h.dtype)
+            grad_h[s:s + chunk] = g @ weight
+            grad_w += (g.t() @ hs).float()
+        ctx.save_for_backward(grad_h, grad_w.to(weight.dtype))
+        return total
+
+    @staticmethod
+    def backward(ctx, g):
+        grad_h, grad_w = ctx.saved_tensors
+        return grad_h * g.to(grad_h.dtype), grad_w * g.to(grad_w.dtype), None, None, None
+
+
+class GPT2DoubleHeads(nn.Module):
+    def __init__(self, cfg: Optional[GPT2Config] = None):
+        super().__init__()
+        self.cfg = cfg = cfg or GPT2Config()
+        # rows padded to a multiple of 64 so the LM-head GEMM and the fused CE kernel see aligned rows;
+        # ids >= vocab_size are never produced and their logits are masked out
+        self.padded_vocab = (cfg.vocab_size + 63) // 64 * 64
+        self.wte = nn.Embedding(self.padded_vocab, cfg.n_embd)
+        self.wpe = nn.Embedding(cfg.n_positions, cfg.n_embd)
+        self.h = nn.ModuleList([Block(cfg) for _ in range(cfg.n_layer)])
+        self.ln_f = nn.LayerNorm(cfg.n_embd, eps=cfg.layer_norm_epsilon)
+        self.mc_head = nn.Linear(cfg.n_embd, 1)           # SequenceSummary(summary_type="cls_index")
+        self.apply(self._init)
+        for blk in self.h:                                  # GPT-2 residual-projection scaling
+            for lin in (blk.c_proj, blk.c_proj2):
+                nn.init.normal_(lin.weight, std=cfg.initializer_range / math.sqrt(2 * cfg.n_layer))
+
+    def _init(self, m):
+        if isinstance(m, (nn.Linear, nn.Embedding)):
+            nn.init.normal_(m.weight, std=self.cfg.initializer_range)
+            if isinstance(m, nn.Linear) and m.bias is not None:
+                nn.init.zeros_(m.bias)
+
+    def num_parameters(self) -> int:
+        return sum(p.numel() for p in self.parameters())
+
+    def hidden(self, input_ids: torch.Tensor, token_type_ids: Optional[torch.Tensor]) -> torch.Tensor:
+        N, T = input_ids.shape
+        pos = torch.arange(T, device=input_ids.device)
+        x = self.wte(input_ids) + self.wpe(pos)[None]
+        if token_type_ids is not None:
+            x = x + self.wte(token_type_ids)
+        for blk in self.h:
+            x = blk(x)
+        return self.ln_f(x)
+
+    def forward(self, input_ids, token_type_ids=None, mc_token_ids=None, lm_labels=None, mc_labels=None,
+                lm_coef: float = 1.0, mc_coef: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """-> (loss, lm_loss, mc_loss). Shapes as in the reference: [B, C, T] ids/labels, [B, C]
+        mc_token_ids, [B] mc_labels; -100 labels are ignored."""
+        B, C, T = input_ids.shape
+        ids = input_ids.reshape(B * C, T)
+        tt = token_type_ids.reshape(B * C, T) if token_type_ids is not None else None
+        h = self.hidden(ids, tt)                                              # [B*C, T, D]
+        zero = torch.zeros((), dtype=torch.float32, device=h.device)
+        lm_loss, mc_loss = zero, zero
+        if lm_labels is not None:
+            labels = lm_labels.reshape(B * C, T)
+            shift_h = h[:, :-1].reshape(-1, h.shape[-1])
+            shift_l = labels[:, 1:].reshape(-1)
+            n_valid = (shift_l >= 0).sum().clamp(min=1)
+            lm_loss = _ChunkedLMLoss.apply(shift_h, self.wte.weight, shift_l, self.cfg.lm_chunk_rows,
+                                           self.cfg.vocab_size) / n_valid
+        if mc_token_ids is not None and mc_labels is not None:
+            idx = mc_token_ids.reshape(B * C, 1, 1).expand(-1, 1, h.shape[-1])
+            cls_h = h.gather(1, idx).squeeze(1)                               # [B*C, D]
+            mc_logits = self.mc_head(cls_h).view(B, C).float()
+            mc_loss = F.cross_entropy(mc_logits, mc_labels)
+        loss = lm_coef * lm_loss + mc_coef * mc_loss
+        return loss, lm_loss, mc_loss
+
+
+def synthetic_batch(batch: int, candidates: int, seq_len: int, vocab: int, device="cpu", seed: int = 0,
+                    pin: bool = False):
+    """PersonaChat-shaped synthetic batch (the real set is downloaded by the reference; there is no
+    network here): history tokens carry -100 labels, only the last candidate's reply is scored."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, vocab, (batch, candidates, seq_len), generator=g)
+    tt = torch.randint(vocab - 5, vocab - 3, (batch, candidates, seq_len), generator=g)
+    labels = torch.full((batch, candidates, seq_len), -100, dtype=torch.long)
+    reply = max(1, seq_len // 4)
+    labels[:, -1, -reply:] = ids[:, -1, -reply:]
+    mc_token_ids = torch.full((batch, candidates), seq_len - 1, dtype=torch.long)
+    mc_labels = torch.full((batch,), candidates - 1, dtype=torch.long)
+    out = {"input_ids": ids, "token_type_ids": tt, "lm_labels": labels, "mc_token_ids": mc_token_ids,
+           "mc_labels": mc_labels}
+    if pin and torch.cuda.is_available():
+        out = {k: v.pin_memory() for k, v in out.items()}
+    if device != "cpu":
+        out = {k: v.to(device, non_blocking=True) for k, v in out.items()}
+    return out

@@ -1,0 +1,87 @@
+"""Hand-written sm_100a ops used by the training engine and the workloads (bound through the same
+in-tree ``libadapcc.so`` as the collectives). Every function launches on the current CUDA stream
+and fails loudly if the native library is missing — there is no silent PyTorch fallback on a GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_float, c_int, c_longlong, c_void_p
+from typing import Optional
+
+import torch
+
+from ..constants import DTYPE_IDS
+from ..runtime.native import NativeError, last_error, load_library
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    lib = load_library()
+    if not _bound:
+        lib.adapcc_sumsq.argtypes = [c_void_p, c_longlong, c_int, c_void_p, c_void_p]
+        lib.adapcc_fused_adamw.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int,
+                                           c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_float,
+                                           c_void_p, c_void_p, c_void_p]
+        lib.adapcc_fused_sgd.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_float, c_float,
+                                         c_void_p]
+        lib.adapcc_incr_int.argtypes = [c_void_p, c_void_p]
+        lib.adapcc_fused_ce.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+        _bound = True
+    return lib
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t: torch.Tensor) -> int:
+    return DTYPE_IDS[str(t.dtype).replace("torch.", "")]
+
+
+def _ck(rc: int, what: str) -> None:
+    if rc != 0:
+        raise NativeError(f"{what} failed: {last_error()}")
+
+
+def sumsq_(grad: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out (1-element fp32, already zeroed) += sum(grad**2)."""
+    _ck(_lib().adapcc_sumsq(c_void_p(grad.data_ptr()), grad.numel(), _dt(grad), c_void_p(out.data_ptr()), _stream()),
+        "sumsq")
+    return out
+
+
+def fused_adamw_(param: torch.Tensor, grad: torch.Tensor, master: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *,
+                 lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01, step: int = 1,
+                 max_norm: float = 0.0, grad_scale: float = 1.0, sumsq: Optional[torch.Tensor] = None,
+                 step_tensor: Optional[torch.Tensor] = None) -> None:
+    """One launch: clip (coefficient derived on the device from ``sumsq``), AdamW on the fp32
+    master/m/v, write-back of the (bf16 or fp32) parameters. ``step_tensor`` (int32 on device) makes
+    the bias correction replayable inside a CUDA graph."""
+    _ck(_lib().adapcc_fused_adamw(c_void_p(param.data_ptr()), c_void_p(grad.data_ptr()), c_void_p(master.data_ptr()),
+                                  c_void_p(m.data_ptr()), c_void_p(v.data_ptr()), param.numel(), _dt(param), _dt(grad),
+                                  lr, betas[0], betas[1], eps, weight_decay, int(step), max_norm, grad_scale,
+                                  c_void_p(sumsq.data_ptr() if sumsq is not None else None),
+                                  c_void_p(step_tensor.data_ptr() if step_tensor is not None else None), _stream()),
+        "fused_adamw")
+
+
+def fused_sgd_(param, grad, master, *, lr: float, grad_scale: float = 1.0) -> None:
+    _ck(_lib().adapcc_fused_sgd(c_void_p(param.data_ptr()), c_void_p(grad.data_ptr()), c_void_p(master.data_ptr()),
+                                param.numel(), _dt(param), _dt(grad), lr, grad_scale, _stream()), "fused_sgd")
+
+
+def incr_(t: torch.Tensor) -> None:
+    _ck(_lib().adapcc_incr_int(c_void_p(t.data_ptr()), _stream()), "incr")
+
+
+def fused_ce_(logits: torch.Tensor, labels: torch.Tensor, vocab: int) -> torch.Tensor:
+    """In place: bf16 ``logits`` [rows, stride] become d(sum of row losses)/d logits; returns the
+    per-row losses (fp32). Rows whose label is negative are ignored (loss 0, zero gradient)."""
+    assert logits.dtype == torch.bfloat16 and logits.is_contiguous() and logits.dim() == 2
+    rows, stride = logits.shape
+    row_loss = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    _ck(_lib().adapcc_fused_ce(c_void_p(logits.data_ptr()), c_void_p(labels.data_ptr()), c_void_p(row_loss.data_ptr()),
+                               rows, int(vocab), stride, _stream()), "fused_ce")
+    return row_loss

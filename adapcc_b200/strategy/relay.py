@@ -19,7 +19,7 @@ from dataclasses import dataclass, field
 from typing import Iterable, List, Sequence, Set
 
 from ..constants import (ALLREDUCE, BOARDCAST, REDUCE, RELAY_BYPASS, RELAY_FORWARD, TR_HAS_LOCAL,
-                         TR_IN_BCAST, TR_IN_REDUCE, TR_PUBLISH, TR_WANT_RESULT)
+                         TR_IN_BCAST, TR_IN_REDUCE, TR_PARENT_IS_ROOT, TR_PUBLISH, TR_WANT_RESULT)
 from .trees import Strategy, Tree
 
 
@@ -81,6 +81,7 @@ def tree_role(tree: Tree, rank: int, active: Iterable[int], prim: int = ALLREDUC
     local = rank in act
     recvs = [c for c in T.kids(rank) if subtree_active(T, c, act)]
     role.parent = -1 if is_root else T.parent.get(rank, -1)
+    pir = TR_PARENT_IS_ROOT if (role.parent >= 0 and role.parent == T.root) else 0
     if prim in (ALLREDUCE, REDUCE):
         if not (local or recvs):
             return TreeRole()
@@ -90,7 +91,7 @@ def tree_role(tree: Tree, rank: int, active: Iterable[int], prim: int = ALLREDUC
         role.children = recvs
         if prim == ALLREDUCE:
             if not is_root:
-                role.flags |= TR_IN_BCAST
+                role.flags |= TR_IN_BCAST | pir
             if local:
                 role.flags |= TR_WANT_RESULT
             if recvs:
@@ -103,7 +104,7 @@ def tree_role(tree: Tree, rank: int, active: Iterable[int], prim: int = ALLREDUC
         else:
             if not (local or recvs):
                 return TreeRole()
-            role.flags |= TR_IN_BCAST
+            role.flags |= TR_IN_BCAST | pir
             if local:
                 role.flags |= TR_WANT_RESULT
             if recvs:

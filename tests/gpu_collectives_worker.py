@@ -59,7 +59,7 @@ def main():
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     name = unique_name("worker")
-    comm = NativeComm(name, rank, world, local, staging_bytes=64 << 20, heap_bytes=128 << 20)
+    comm = NativeComm(name, rank, world, local, staging_bytes=256 << 20, heap_bytes=512 << 20)
     if rank == 0:
         print(f"[worker] world={world} symm={comm.symm_backend} multicast={comm.multicast} "
               f"heap_mc={comm.heap_multicast}", flush=True)
@@ -243,44 +243,90 @@ def main():
     results = []
     if args.sweep:
         comm.load_strategy(strategies["binary"])
-        big = comm.symm_empty if False else None
-        sweep_sizes = [1 << p for p in range(10, 28, 2 if args.quick else 1)]  # bytes
-        def timeit(fn, iters, warm=5):
-            for _ in range(warm):
-                fn()
-            torch.cuda.synchronize(); dist.barrier()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            for _ in range(iters):
-                fn()
-            e.record(); torch.cuda.synchronize()
-            t = torch.tensor([s.elapsed_time(e) / iters], device=dev)
+        sweep_sizes = [1 << p for p in range(10, 29 if not args.quick else 27, 2 if args.quick else 1)]  # bytes
+        side = torch.cuda.Stream()
+
+        def timeit(fn, iters, graph=True):
+            """Device time per call, max over ranks. graph=True replays a captured CUDA graph of
+            `iters` back-to-back calls, so Python/launch overhead is excluded for both NCCL and us."""
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    fn()
+                side.synchronize()
+                g = None
+                if graph:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        for _ in range(iters):
+                            fn()
+                    g.replay()
+                    side.synchronize()
+                best = 1e9
+                for _ in range(3):
+                    dist.barrier()
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record(side)
+                    if g is not None:
+                        g.replay()
+                    else:
+                        for _ in range(iters):
+                            fn()
+                    e.record(side)
+                    side.synchronize()
+                    best = min(best, s.elapsed_time(e) / iters)
+            t = torch.tensor([best], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return t.item() * 1e-3
+
         for nbytes in sweep_sizes:
             n = nbytes // 4
             x = torch.randn(n, device=dev)
             comm.heap_reset()
             hz = comm.symm_empty(n, torch.float32) if nbytes <= comm.heap_bytes else None
-            iters = 50 if nbytes <= (1 << 22) else 15
+            iters = 40 if nbytes <= (1 << 22) else (10 if nbytes <= (1 << 26) else 4)
             row = {"bytes": nbytes}
             row["nccl"] = timeit(lambda: dist.all_reduce(x), iters)
+            row["nccl_eager"] = timeit(lambda: dist.all_reduce(x), iters, graph=False)
             for algo in algos + ["auto"]:
                 if algo == "one_shot" and nbytes > (4 << 20):
                     continue
                 row[algo] = timeit(lambda: comm.all_reduce(x, algo=algo), iters)
                 if hz is not None and algo not in ("one_shot",):
                     row[algo + "_zc"] = timeit(lambda: comm.all_reduce(hz, algo=algo), iters)
+            row["auto_eager"] = timeit(lambda: comm.all_reduce(x, algo="auto"), iters, graph=False)
             row["bf16wire_auto"] = timeit(lambda: comm.all_reduce(x, algo="auto", wire="bfloat16"), iters)
             if nbytes >= (1 << 16):
-                row["tree"] = timeit(lambda: comm.tree_collective(ALLREDUCE, x, chunk_bytes=max(16, min(1 << 20, nbytes // 8))), iters)
+                row["tree"] = timeit(lambda: comm.tree_collective(ALLREDUCE, x, chunk_bytes=4 << 20), iters)
             comm.check()
             results.append(row)
             if rank == 0:
                 f = 2 * (world - 1) / world
                 print("[sweep] %10d B " % nbytes + " ".join(
-                    f"{k}={v * 1e6:8.1f}us({nbytes * f / v / 1e9:6.1f}GB/s)" for k, v in row.items() if k != "bytes"),
+                    f"{k}={v * 1e6:7.1f}us({nbytes * f / v / 1e9:6.1f})" for k, v in row.items() if k != "bytes"),
                     flush=True)
+        # CTA-count sensitivity at large sizes (zero-copy paths)
+        for nbytes in [1 << 24, 1 << 26]:
+            n = nbytes // 4
+            comm.heap_reset()
+            hz = comm.symm_empty(n, torch.float32)
+            for blocks in [16, 32, 64, 96, 128, 148]:
+                comm.set_tunable("max_blocks", blocks)
+                comm.set_tunable("tree_blocks", blocks)
+                row = {"bytes": nbytes, "blocks": blocks}
+                for algo in [a for a in algos if a != "one_shot"]:
+                    row[algo + "_zc"] = timeit(lambda: comm.all_reduce(hz, algo=algo), 8)
+                x = torch.randn(n, device=dev)
+                row["two_shot"] = timeit(lambda: comm.all_reduce(x, algo="two_shot"), 8)
+                row["tree"] = timeit(lambda: comm.tree_collective(ALLREDUCE, x, chunk_bytes=4 << 20), 8)
+                comm.check()
+                results.append(row)
+                if rank == 0:
+                    f = 2 * (world - 1) / world
+                    print(f"[blocks] {nbytes} B blocks={blocks} " + " ".join(
+                        f"{k}={v * 1e6:7.1f}us({nbytes * f / v / 1e9:6.1f})" for k, v in row.items()
+                        if k not in ("bytes", "blocks")), flush=True)
+            comm.set_tunable("max_blocks", 64)
+            comm.set_tunable("tree_blocks", 64)
     if rank == 0 and args.out:
         os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
         with open(args.out, "w") as fh:
