@@ -21,6 +21,7 @@ extern "C" {
 const char* adapcc_last_error() { return get_error(); }
 
 int adapcc_version() { return 100; }
+long long adapcc_launch_count() { return launch_count(); }
 
 void* adapcc_ctx_create(const char* name, int rank, int world, int device, unsigned long long staging_bytes,
                         unsigned long long heap_bytes) {
@@ -73,6 +74,7 @@ int adapcc_ctx_set_tunable(void* h, int key, long long value) {
     case 5: c->tun.tree_blocks = (int)std::max<long long>(1, std::min<long long>(value, kMaxBlocks)); break;
     case 6: c->tun.tree_chunk_max_bytes = value; break;
     case 7: c->tun.nvls_min_ranks = (int)value; break;
+    case 8: c->tun.force_kernel = (int)value; break;
     default: set_error("unknown tunable %d", key); return -1;
   }
   return 0;
@@ -117,6 +119,44 @@ int adapcc_ctx_check(void* h, void* stream) { return static_cast<CommContext*>(h
 int adapcc_ctx_host_barrier(void* h) {
   CommContext* c = static_cast<CommContext*>(h);
   return c->world() > 1 ? c->symm().boot().barrier() : 0;
+}
+
+// ---- symmetric-heap allocator for torch.cuda.MemPool (CUDAPluggableAllocator ABI) ---------------
+// DDP gradient buckets allocated inside `use_mem_pool` land in the symmetric heap, which makes
+// the comm hook's all-reduce zero-copy. Bump allocation: every rank performs the same sequence of
+// allocations, so offsets match across ranks; blocks are returned when the context is destroyed.
+namespace {
+std::mutex g_pool_mu;
+CommContext* g_pool_ctx = nullptr;
+size_t g_pool_off = 0;
+size_t g_pool_limit = 0;
+}  // namespace
+
+int adapcc_pool_bind(void* h, unsigned long long start_offset) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_pool_ctx = static_cast<CommContext*>(h);
+  g_pool_off = (size_t)start_offset;
+  g_pool_limit = g_pool_ctx ? g_pool_ctx->heap_bytes() : 0;
+  return 0;
+}
+unsigned long long adapcc_pool_offset() {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  return g_pool_off;
+}
+void* adapcc_pool_alloc(ssize_t size, int device, void* stream) {
+  (void)device; (void)stream;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (!g_pool_ctx || !g_pool_ctx->heap_ptr()) { set_error("pool_alloc: no symmetric heap bound"); return nullptr; }
+  size_t off = (g_pool_off + 511) & ~(size_t)511;
+  if (off + (size_t)size > g_pool_limit) {
+    set_error("pool_alloc: symmetric heap exhausted (%zu + %zd > %zu); raise heap_mb", off, size, g_pool_limit);
+    return nullptr;
+  }
+  g_pool_off = off + (size_t)size;
+  return (char*)g_pool_ctx->heap_ptr() + off;
+}
+void adapcc_pool_free(void* ptr, ssize_t size, int device, void* stream) {
+  (void)ptr; (void)size; (void)device; (void)stream;   // bump allocator: reclaimed with the context
 }
 
 // ---- strategy / relay-control queries (no GPU needed; used by tests and the control plane)

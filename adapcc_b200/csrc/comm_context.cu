@@ -51,6 +51,7 @@ int launch_direct_nr(int algo, int blocks, cudaStream_t s, const DevComm& dc, co
       return -1;
   }
   CUDA_TRY(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -62,6 +63,8 @@ int launch_direct(int algo, int blocks, cudaStream_t s, const DevComm& dc, const
   if (algo == NVLS) {
     allreduce_direct_kernel<U, W, OP, NVLS, 2><<<blocks, kThreads, 0, s>>>(dc, i, o, n, scale, flags, root);
     CUDA_TRY(cudaGetLastError());
+    count_launch();
+  count_launch();
     return 0;
   }
   const int na = dc.n_active;
@@ -184,6 +187,7 @@ int CommContext::skip_op(cudaStream_t stream) {
   if (fill_comm({}, w, &dc)) return -1;
   skip_op_kernel<<<1, 32, 0, stream>>>(dc);
   CUDA_TRY(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -204,7 +208,7 @@ int CommContext::reduce(const void* in, void* out, long long count, int dtype, i
     flags |= F_ROOT_ONLY;
   }
   const size_t esize = dtype_size(dtype), wsize = dtype_size(wire);
-  if (na == 1) {
+  if (na == 1 && !tun.force_kernel) {
     if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, (size_t)count * esize, cudaMemcpyDeviceToDevice, stream));
     return skip_op(stream);
   }
@@ -262,7 +266,7 @@ int CommContext::broadcast(void* buf, long long count, int dtype, int root, cons
   for (int i = 0; i < na; ++i)
     if (active[i] == root) root_index = i;
   if (root_index < 0) { set_error("broadcast root %d is not in the active list", root); return -1; }
-  if (na == 1) return skip_op(stream);
+  if (na == 1 && !tun.force_kernel) return skip_op(stream);
   const size_t esize = dtype_size(dtype);
   Window w = resolve(buf, buf, (size_t)count * esize, true);
   const int wire = dtype;
@@ -283,6 +287,9 @@ int CommContext::broadcast(void* buf, long long count, int dtype, int root, cons
     int rc = ADAPCC_DISPATCH_TYPES(dtype, wire, {
       broadcast_direct_kernel<U, W><<<blocks, kThreads, 0, stream>>>(dc, (U*)p, n, root_index, use_mc, flags);
       CUDA_TRY(cudaGetLastError());
+    count_launch();
+      count_launch();
+  count_launch();
       return 0;
     });
     if (rc) return rc;
@@ -374,11 +381,31 @@ int CommContext::tree_collective(int prim, const void* in, void* out, long long 
       else
         tree_collective_kernel<U, W, SUM><<<blocks, kThreads, 0, stream>>>(dc, plan, (const U*)pin, (U*)pout, n, scale);
       CUDA_TRY(cudaGetLastError());
+    count_launch();
+      count_launch();
+  count_launch();
       return 0;
     });
     if (rc) return rc;
     done += n;
   }
+  return 0;
+}
+
+namespace adapcc_detail { void launch_barrier(const DevComm& dc, cudaStream_t s); }
+
+int CommContext::device_barrier(const std::vector<int>& active, cudaStream_t stream) {
+  if (!inited_) { set_error("context not initialised"); return -1; }
+  const bool mine = std::find(active.begin(), active.end(), rank_) != active.end();
+  if (!mine || active.size() <= 1) return skip_op(stream);
+  std::vector<int> act(active);
+  std::sort(act.begin(), act.end());
+  DevComm dc;
+  Window w = resolve(nullptr, nullptr, 0, false);
+  if (fill_comm(act, w, &dc)) return -1;
+  adapcc_detail::launch_barrier(dc, stream);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

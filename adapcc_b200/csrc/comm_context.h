@@ -21,6 +21,7 @@ struct Tunables {
   int nvls_min_ranks = 3;              // NVLS only pays off when >2 ranks share the switch reduction
   int relay_mode = RELAY_FORWARD;
   long long timeout_ms = 30000;
+  int force_kernel = 0;                // run kernels even for a single participant (smoke / ncu)
   int tree_blocks = 128;                // CTAs of the tree kernel (half reduce, half broadcast)
   long long tree_chunk_max_bytes = 256 << 10;  // device pipelining granularity (wire bytes)
 };
@@ -48,6 +49,8 @@ class CommContext {
                       int op, long long chunk_bytes, const std::vector<int>& active,
                       cudaStream_t stream);
   int skip_op(cudaStream_t stream);
+  // One-CTA device barrier among `active` (orders peer stores before peer loads across kernels).
+  int device_barrier(const std::vector<int>& active, cudaStream_t stream);
 
   // Reads (and clears) the sticky device error word; synchronises the stream.
   int check(cudaStream_t stream);

@@ -66,4 +66,8 @@ int log_level();
 
 const char* cu_error_string(CUresult r);
 
+// Number of kernels this library has launched (bench.py reports it as gpu_launches).
+void count_launch(int n = 1);
+long long launch_count();
+
 }  // namespace adapcc

@@ -1,6 +1,7 @@
 #include "driver_api.h"
 
 #include <cstdarg>
+#include <atomic>
 #include <mutex>
 
 namespace adapcc {
@@ -15,6 +16,10 @@ void set_error(const char* fmt, ...) {
   if (log_level() >= 1) fprintf(stderr, "[adapcc][error] %s\n", g_err);
 }
 const char* get_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int log_level() {
   static int lvl = [] {

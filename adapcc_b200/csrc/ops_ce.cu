@@ -99,5 +99,6 @@ extern "C" int adapcc_fused_ce(void* logits, const long long* labels, float* row
   if (vocab > stride) { set_error("fused_ce: vocab > stride"); return -1; }
   fused_ce_kernel<<<rows, 512, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)logits, labels, row_loss, vocab, stride);
   CUDA_TRY(cudaGetLastError());
+  count_launch();
   return 0;
 }

@@ -147,6 +147,7 @@ int adapcc_sumsq(const void* g, long long n, int dtype, float* out, void* stream
   else if (dtype == BF16) sumsq_kernel<__nv_bfloat16><<<blocks, 512, 0, s>>>((const __nv_bfloat16*)g, n, out);
   else { set_error("sumsq: unsupported dtype %d", dtype); return -1; }
   CUDA_TRY(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -179,6 +180,7 @@ int adapcc_fused_adamw(void* param, const void* grad, float* master, float* m, f
     adamw_kernel<float, __nv_bfloat16><<<blocks, 512, 0, s>>>((float*)param, (const __nv_bfloat16*)grad, master, m, v, n, a, sumsq, step_ptr);
   else { set_error("adamw: unsupported dtypes %d/%d", param_dtype, grad_dtype); return -1; }
   CUDA_TRY(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -187,6 +189,7 @@ __global__ void incr_int_kernel(int* p) { if (threadIdx.x == 0 && blockIdx.x == 
 int adapcc_incr_int(int* p, void* stream) {
   incr_int_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
   CUDA_TRY(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -201,6 +204,7 @@ int adapcc_fused_sgd(void* param, const void* grad, float* master, long long n, 
     sgd_kernel<float, float><<<blocks, 512, 0, s>>>((float*)param, (const float*)grad, master, n, lr, grad_scale);
   else { set_error("sgd: unsupported dtypes %d/%d", param_dtype, grad_dtype); return -1; }
   CUDA_TRY(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

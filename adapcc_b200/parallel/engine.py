@@ -1,0 +1,193 @@
+"""Flat-buffer data-parallel training engine (the B200-native fast path next to the DDP hook).
+
+The reference drives gradient communication through torch DDP buckets and a *blocking* hook
+(/root/reference/train_ddp.py:35-41, /root/reference/commu.py:385-435). This engine keeps the same
+semantics — synchronous data parallelism, bucketed gradient all-reduce overlapped with backward,
+mean over the active ranks, clip + AdamW — but lays memory out for the hardware:
+
+* all parameters are views into ONE flat bf16 buffer, all gradients views into ONE flat buffer that
+  lives in the communicator's **symmetric heap**, so a bucket's all-reduce is zero-copy: peers read
+  and write the gradient bucket directly over NVLink (two-shot) or the switch reduces it in flight
+  (NVLS ``multimem.ld_reduce``), with the 1/N scale fused — no staging, no cast kernel, no NCCL;
+* buckets are launched from ``post_accumulate_grad`` hooks onto a high-priority side stream as soon
+  as their last gradient is produced (overlap with the rest of backward);
+* the optimizer is two launches over the flat buffers (grad-norm reduction + fused clip/AdamW with
+  fp32 master weights);
+* the whole step — forward, backward, the collective kernels on the forked stream, optimizer — is
+  captured once into a CUDA graph and replayed, which our kernels allow because their flag epochs
+  live in device memory (nothing host-computed is baked into a launch).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+
+@dataclass
+class _Bucket:
+    start: int          # element offsets into the flat buffers
+    end: int
+    n_params: int
+    pending: int = 0
+
+
+class FlatDataParallel:
+    def __init__(self, model: nn.Module, comm=None, *, world_size: int = 1, rank: int = 0,
+                 bucket_mb: float = 32.0, lr: float = 6.25e-5, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.01, max_norm: float = 1.0, optimizer: str = "adamw",
+                 param_dtype: torch.dtype = torch.bfloat16, algo: str = "auto", active: Optional[Sequence[int]] = None,
+                 comm_fn: Optional[Callable] = None):
+        """``comm``: a :class:`~adapcc_b200.runtime.native.NativeComm` (or None for one GPU).
+        ``comm_fn(flat_slice)``: alternative collective (e.g. an NCCL all-reduce) for baselines."""
+        self.model, self.comm, self.world_size, self.rank = model, comm, world_size, rank
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        self.optimizer, self.algo, self.comm_fn = optimizer, algo, comm_fn
+        self.active = list(active) if active is not None else list(range(world_size))
+        self.device = next(model.parameters()).device
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.params = params
+        total = sum((p.numel() + 7) // 8 * 8 for p in params)       # every view 16-byte aligned
+        self.total = total
+        dev = self.device
+        # ---- flat parameter / gradient / optimizer state ---------------------------------------
+        self.flat_param = torch.zeros(total, dtype=param_dtype, device=dev)
+        esize = self.flat_param.element_size()
+        self.zero_copy = False
+        if comm is not None and world_size > 1 and comm.heap_bytes >= total * esize + 4096:
+            self.flat_grad = comm.symm_empty(total, param_dtype)
+            self.flat_grad.zero_()
+            self.zero_copy = True
+        else:
+            self.flat_grad = torch.zeros(total, dtype=param_dtype, device=dev)
+        self.master = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.step_t = torch.zeros(1, dtype=torch.int32, device=dev)
+        off = 0
+        self._offsets: List[int] = []
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                self.master[off:off + n].copy_(p.detach().reshape(-1).float())
+                view = self.flat_param[off:off + n].view_as(p)
+                view.copy_(p.detach())
+                p.data = view
+                p.grad = self.flat_grad[off:off + n].view_as(p)
+                self._offsets.append(off)
+                off += (n + 7) // 8 * 8
+        # ---- buckets: contiguous ranges, filled from the LAST parameter backwards (gradients are
+        # produced roughly in reverse registration order) ------------------------------------------
+        cap = max(1, int(bucket_mb * (1 << 20) / esize))
+        self.buckets: List[_Bucket] = []
+        self._bucket_of: Dict[int, int] = {}
+        end, members = total, []
+        for i in range(len(params) - 1, -1, -1):
+            members.append(i)
+            start = self._offsets[i]
+            if end - start >= cap or i == 0:
+                for j in members:
+                    self._bucket_of[j] = len(self.buckets)
+                self.buckets.append(_Bucket(start, end, len(members)))
+                end, members = start, []
+        self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(params)]
+        self.comm_stream = torch.cuda.Stream(device=dev, priority=-1) if dev.type == "cuda" else None
+        self._graph = None
+        self._static: Dict[str, torch.Tensor] = {}
+        self._static_loss = None
+        self.steps_done = 0
+        self.native_launches_per_step = 0
+
+    # -- gradient hooks ---------------------------------------------------------------------------
+    def _make_hook(self, i: int):
+        def hook(_p):
+            b = self.buckets[self._bucket_of[i]]
+            b.pending -= 1
+            if b.pending == 0:
+                self._launch_bucket(b)
+        return hook
+
+    def _launch_bucket(self, b: _Bucket) -> None:
+        if self.world_size <= 1 or (self.comm is None and self.comm_fn is None):
+            return
+        cur = torch.cuda.current_stream(self.device)
+        self.comm_stream.wait_stream(cur)
+        self._forked = True
+        with torch.cuda.stream(self.comm_stream):
+            seg = self.flat_grad[b.start:b.end]
+            if self.comm_fn is not None:
+                self.comm_fn(seg)
+            else:
+                self.comm.all_reduce(seg, op="avg", algo=self.algo, active=self.active)
+
+    # -- one training step -------------------------------------------------------------------------
+    def _step_body(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        from ..ops import fused_adamw_, fused_sgd_, incr_, sumsq_
+
+        self.flat_grad.zero_()
+        self._forked = False
+        for b in self.buckets:
+            b.pending = b.n_params
+        out = self.model(**batch)
+        loss = out[0] if isinstance(out, (tuple, list)) else out
+        loss.backward()
+        cur = torch.cuda.current_stream(self.device)
+        if self._forked:                              # join the collective stream (also under capture)
+            cur.wait_stream(self.comm_stream)
+        incr_(self.step_t)
+        if self.optimizer == "adamw":
+            sumsq = None
+            if self.max_norm and self.max_norm > 0:
+                self.sumsq.zero_()
+                sumsq_(self.flat_grad, self.sumsq)
+                sumsq = self.sumsq
+            fused_adamw_(self.flat_param, self.flat_grad, self.master, self.exp_avg, self.exp_avg_sq, lr=self.lr,
+                         betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, step=self.steps_done + 1,
+                         max_norm=self.max_norm or 0.0, sumsq=sumsq, step_tensor=self.step_t)
+        else:
+            fused_sgd_(self.flat_param, self.flat_grad, self.master, lr=self.lr)
+        return loss.detach()
+
+    def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Eager step on device-resident inputs. Returns the (device) loss."""
+        loss = self._step_body(batch)
+        self.steps_done += 1
+        return loss
+
+    # -- CUDA graph ---------------------------------------------------------------------------------
+    def capture(self, example_batch: Dict[str, torch.Tensor], warmup: int = 2) -> None:
+        """Capture one full step. ``example_batch`` fixes the shapes; later steps copy their inputs
+        into the static buffers (``step_graph``)."""
+        from ..runtime.native import load_library
+
+        self._static = {k: v.clone() for k, v in example_batch.items()}
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):                       # allocator + cuBLAS workspaces settle
+                self._step_body(self._static)
+                self.steps_done += 1
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        lib = load_library()
+        c0 = lib.adapcc_launch_count() if hasattr(lib, "adapcc_launch_count") else 0
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self._step_body(self._static)
+        self.native_launches_per_step = (lib.adapcc_launch_count() - c0) if hasattr(lib, "adapcc_launch_count") else 0
+
+    def step_graph(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Copy ``batch`` (pinned host or device tensors) into the static inputs and replay."""
+        for k, v in batch.items():
+            self._static[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        self.steps_done += 1
+        return self._static_loss
+
+    def close(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._graph = None

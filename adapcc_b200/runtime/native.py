@@ -43,6 +43,7 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
             _build.build()
         lib = ctypes.CDLL(str(_LIB_PATH), mode=ctypes.RTLD_GLOBAL)
         lib.adapcc_last_error.restype = c_char_p
+        lib.adapcc_launch_count.restype = c_longlong
         lib.adapcc_ctx_create.restype = c_void_p
         lib.adapcc_ctx_create.argtypes = [c_char_p, c_int, c_int, c_int, c_ulonglong, c_ulonglong]
         lib.adapcc_ctx_destroy.argtypes = [c_void_p]
@@ -58,6 +59,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
         lib.adapcc_ctx_peer_staging_ptr.restype = c_void_p
         lib.adapcc_ctx_peer_staging_ptr.argtypes = [c_void_p, c_int]
         lib.adapcc_ctx_last_algo.argtypes = [c_void_p]
+        lib.adapcc_pool_bind.argtypes = [c_void_p, c_ulonglong]
+        lib.adapcc_pool_offset.restype = c_ulonglong
         lib.adapcc_ctx_set_tunable.argtypes = [c_void_p, c_int, c_longlong]
         lib.adapcc_ctx_load_strategy.argtypes = [c_void_p, c_char_p]
         lib.adapcc_ctx_load_strategy_text.argtypes = [c_void_p, c_char_p]
@@ -95,7 +98,7 @@ def _int_array(values: Sequence[int]):
 
 
 TUNABLE_KEYS = {"max_blocks": 0, "one_shot_max_bytes": 1, "nvls_min_bytes": 2, "relay_mode": 3,
-                "timeout_ms": 4, "tree_blocks": 5, "tree_chunk_max_bytes": 6, "nvls_min_ranks": 7}
+                "timeout_ms": 4, "tree_blocks": 5, "tree_chunk_max_bytes": 6, "nvls_min_ranks": 7, "force_kernel": 8}
 
 
 class _CudaArray:
@@ -190,6 +193,24 @@ class NativeComm:
 
     def heap_reset(self) -> None:
         self._heap_off = 0
+
+    def mem_pool(self):
+        """A ``torch.cuda.MemPool`` whose blocks come from this context's symmetric heap. Tensors
+        allocated under ``torch.cuda.use_mem_pool(pool)`` (e.g. DDP's gradient buckets) are then
+        reduced zero-copy. Every rank must allocate the same sequence of sizes."""
+        import torch
+
+        if getattr(self, "_pool", None) is None:
+            self.lib.adapcc_pool_bind(self.handle, (self._heap_off + 511) // 512 * 512)
+            alloc = torch.cuda.memory.CUDAPluggableAllocator(str(lib_path()), "adapcc_pool_alloc", "adapcc_pool_free")
+            self._pool_allocator = alloc
+            self._pool = torch.cuda.MemPool(alloc.allocator())
+        return self._pool
+
+    def in_heap(self, tensor) -> bool:
+        base = self.lib.adapcc_ctx_heap_ptr(self.handle) or 0
+        p = tensor.data_ptr()
+        return bool(base) and base <= p and p + tensor.numel() * tensor.element_size() <= base + self.heap_bytes
 
     # -- collectives ---------------------------------------------------------------------
     @staticmethod

@@ -1,0 +1,28 @@
+"""Multi-GPU numerics of every collective kernel variant (one-shot / two-shot / NVLS / trees /
+relay subsets / zero-copy) against fp32 references: spawns tests/gpu_collectives_worker.py under
+torchrun on min(#GPUs, 4) ranks. Skipped on boxes with a single GPU (the single-GPU kernel paths are
+covered by tests/test_gpu_ops.py)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_collectives_multi_gpu():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 4 if n >= 4 else 2
+    env = dict(os.environ, ADAPCC_TIMEOUT_MS="15000")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29517",
+           os.path.join(ROOT, "tests", "gpu_collectives_worker.py"), "--quick"]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    tail = (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0, tail
+    assert "failures: 0" in r.stdout, tail

@@ -1,0 +1,90 @@
+"""Synthesizer: ParTrees parity, MILP (HiGHS) really solves and emits XML, cost model sanity."""
+import os
+
+import pytest
+
+from adapcc_b200.strategy import Strategy
+from adapcc_b200.synth import (LinkModel, ParTrees, Solver, Synthesizer, crossover_bytes, direct_times,
+                               pick_algorithm, strategy_time)
+
+
+def _uniform(world, bw=700.0, lat=2.0):
+    lm = LinkModel.uniform(world, lat, bw)
+    return lm.bw_gbs, lm.alpha_us
+
+
+def test_partrees_reference_shape_two_servers(tmp_path):
+    """Reference semantics (/root/reference/gurobi/trees.py:110-152): one node per server, binary tree
+    across servers, chain inside each server, parallel_degree = min(#servers, degree)."""
+    ips = ["a"] * 4 + ["b"] * 4
+    bw, lat = _uniform(8)
+    sf = tmp_path / "s.xml"
+    chunk = ParTrees("chain").optimize(ips, [0, 4], "reduce", 4, 25_000_000, bw, lat, str(sf))
+    assert chunk > 0
+    s = Strategy.from_file(sf)
+    assert len(s.trees) == 2 and {t.root for t in s.trees} == {0, 4}
+    t = next(t for t in s.trees if t.root == 0)
+    assert t.kids(0) == [1, 4] and t.kids(1) == [2] and t.kids(2) == [3]      # chain + cross-server child
+    assert t.kids(4) == [5] and t.ip[4] == "b"
+    s.validate(8)
+
+
+def test_partrees_single_server_rotates_roots(tmp_path):
+    bw, lat = _uniform(8)
+    s = ParTrees("binary").build(["h"] * 8, [0], 4, bw, lat)
+    assert len(s.trees) == 4 and len({t.root for t in s.trees}) == 4
+    s.validate(8)
+    assert max(t.depth() for t in s.trees) == 4
+
+
+def test_milp_solver_emits_valid_strategy(tmp_path):
+    pytest.importorskip("scipy")
+    bw, lat = _uniform(8)
+    # make rank 7's links slow: the solver must not hang subtrees off it
+    for i in range(8):
+        bw[i][7] = bw[7][i] = 100.0 if i != 7 else 0.0
+    sf = tmp_path / "milp.xml"
+    sol = Solver(time_limit_s=10.0)
+    chunk = sol.optimize("reduce", 4, 25_000_000, bw, lat, str(sf), ip_table=["h"] * 8)
+    assert chunk >= 16 and os.path.exists(sf)
+    s = Strategy.from_file(sf)
+    s.validate(8)
+    assert len(s.trees) == 4 and len({t.root for t in s.trees}) == 4
+    assert all(len(t.kids(7)) <= 1 for t in s.trees), "slow rank should be (near) a leaf"
+    assert "est_us" in s.attrs
+
+
+def test_synthesizer_api_parity_and_policies(tmp_path):
+    bw, lat = _uniform(4)
+    sf = tmp_path / "auto.xml"
+    syn = Synthesizer(str(sf), ip_table=["h"] * 4, parallel_degree=2, size=1_000_000, policy="auto")
+    syn.set_bandwidth_graph(bw)
+    syn.set_latency_graph(lat)
+    syn.set_parallel_degree(2)
+    syn.set_transmission_size(2_000_000)
+    syn.set_ip_info(["h"] * 4)
+    assert syn.local_rank0_list == [0]
+    chunk = syn.generate_strategy("reduce")
+    assert chunk > 0 and syn.last_report["chosen"]
+    Strategy.from_file(sf).validate(4)
+    assert syn.generate_strategy("allgather") is None         # out of the formulation scope
+    syn.policy = "par-trees"
+    assert syn.generate_strategy("broadcast") > 0
+    syn.policy = "gurobi"                                      # reference name for the MILP
+    assert syn.generate_strategy("reduce") > 0
+
+
+def test_cost_model_orders_algorithms():
+    lm = LinkModel.uniform(8, 2.0, 700.0)
+    assert pick_algorithm(lm, 1 << 10) == "one_shot"
+    assert pick_algorithm(lm, 1 << 28) == "nvls"
+    assert pick_algorithm(lm, 1 << 28, nvls=False) == "two_shot"
+    x = crossover_bytes(lm, "one_shot", "two_shot", nvls=False)
+    assert (1 << 14) <= x <= (1 << 22)
+    t = direct_times(lm, 1 << 26)
+    assert t["nvls"] < t["two_shot"] < t["one_shot"]
+    from adapcc_b200.strategy import make_strategy
+
+    deep = strategy_time(make_strategy(8, 1, "chain"), lm, 1 << 26, 1 << 20)
+    wide = strategy_time(make_strategy(8, 4, "binary"), lm, 1 << 26, 1 << 20)
+    assert wide < deep
