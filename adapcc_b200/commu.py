@@ -238,15 +238,25 @@ class CudaCommu:
 
         _, relay_stream = self._streams()
         with torch.cuda.device(self.local_rank), torch.cuda.stream(relay_stream):
-            for i, (numel, chunk_bytes, dtype) in enumerate(self.bucket_info):
-                if self._resolve_algo(numel, dtype, active) == "tree" and self.relay_mode == RELAY_FORWARD:
-                    buf = self.relay_buffer[i]
-                    self.native.tree_collective(ALLREDUCE, buf[:numel], op=self.reduce_op, wire=self._wire_for(dtype),
-                                                chunk_bytes=chunk_bytes, active=active)
-                    self.relay_results.append(buf)
-                else:
-                    self.native.skip_op()       # direct algorithms never route through a relay
-                self.relay_signal_queue.put(step)
+            tree = [self._resolve_algo(n, dt, active) == "tree" for n, _, dt in self.bucket_info]
+            wires = {self._wire_for(dt) or str(dt).replace("torch.", "") for _, _, dt in self.bucket_info}
+            if all(tree) and self.relay_mode == RELAY_FORWARD and len(wires) == 1:
+                # one persistent kernel forwards the chunks of every bucket of this step
+                self.native.tree_relay_persistent([n for n, _, _ in self.bucket_info],
+                                                  [c for _, c, _ in self.bucket_info], wire=wires.pop(),
+                                                  op=self.reduce_op, active=active)
+                for _ in self.bucket_info:
+                    self.relay_signal_queue.put(step)
+            else:
+                for i, (numel, chunk_bytes, dtype) in enumerate(self.bucket_info):
+                    if tree[i] and self.relay_mode == RELAY_FORWARD:
+                        buf = self.relay_buffer[i]
+                        self.native.tree_collective(ALLREDUCE, buf[:numel], op=self.reduce_op,
+                                                    wire=self._wire_for(dtype), chunk_bytes=chunk_bytes, active=active)
+                        self.relay_results.append(buf)
+                    else:
+                        self.native.skip_op()       # direct algorithms never route through a relay
+                    self.relay_signal_queue.put(step)
         relay_stream.synchronize()
 
     # ==========================================================================================

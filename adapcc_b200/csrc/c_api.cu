@@ -114,6 +114,11 @@ int adapcc_tree_collective(void* h, int prim, const void* in, void* out, long lo
   return static_cast<CommContext*>(h)->tree_collective(prim, in, out, count, dtype, wire, op, chunk_bytes,
                                                        sorted_active(active, n_active), (cudaStream_t)stream);
 }
+int adapcc_tree_relay_persistent(void* h, int n_buckets, const long long* counts, const long long* chunk_bytes,
+                                 int wire, int op, const int* active, int n_active, void* stream) {
+  return static_cast<CommContext*>(h)->tree_relay_persistent(n_buckets, counts, chunk_bytes, wire, op,
+                                                             sorted_active(active, n_active), (cudaStream_t)stream);
+}
 int adapcc_skip_op(void* h, void* stream) { return static_cast<CommContext*>(h)->skip_op((cudaStream_t)stream); }
 int adapcc_ctx_check(void* h, void* stream) { return static_cast<CommContext*>(h)->check((cudaStream_t)stream); }
 int adapcc_ctx_host_barrier(void* h) {

@@ -111,6 +111,9 @@ void CommContext::destroy() {
   symm_.free(&sig_);
   if (d_state_) cudaFree(d_state_);
   d_state_ = nullptr;
+  if (d_relay_work_) cudaFree(d_relay_work_);
+  d_relay_work_ = nullptr;
+  relay_work_cap_ = 0;
   symm_.destroy();
 }
 
@@ -389,6 +392,113 @@ int CommContext::tree_collective(int prim, const void* in, void* out, long long 
     if (rc) return rc;
     done += n;
   }
+  return 0;
+}
+
+int CommContext::tree_relay_persistent(int n_buckets, const long long* counts, const long long* chunk_bytes_in,
+                                       int wire, int op, const std::vector<int>& active, cudaStream_t stream) {
+  if (!inited_) { set_error("context not initialised"); return -1; }
+  if (strategy_.trees.empty()) { set_error("relay without a loaded strategy"); return -1; }
+  if (n_buckets <= 0) return 0;
+  if (std::find(active.begin(), active.end(), rank_) != active.end()) {
+    set_error("tree_relay_persistent: rank %d is active; relays only", rank_);
+    return -1;
+  }
+  std::vector<bool> act(world_, false);
+  for (int r : active) {
+    if (r < 0 || r >= world_) { set_error("active rank %d out of range", r); return -1; }
+    act[r] = true;
+  }
+  const int nt = (int)strategy_.trees.size();
+  const int epp = epp_of(wire);
+  const long long cap_elems = (long long)(staging_.size / 16) * epp;
+  bool fits = true;
+  for (int i = 0; i < n_buckets; ++i) fits &= counts[i] <= cap_elems;
+  std::vector<int> participants;
+  std::vector<HostTreeRole> mine(nt);
+  for (int r = 0; r < world_; ++r) {
+    bool any = false;
+    for (int t = 0; t < nt; ++t) {
+      HostTreeRole role = tree_role(strategy_.trees[t], r, act, ALLREDUCE, tun.relay_mode);
+      any |= role.any();
+      if (r == rank_) mine[t] = role;
+    }
+    if (any) participants.push_back(r);
+  }
+  const bool me_in = std::find(participants.begin(), participants.end(), rank_) != participants.end();
+  if (!me_in || !fits) {
+    // nothing routes through this rank (or a bucket needs several pieces): plain per-bucket path
+    for (int i = 0; i < n_buckets; ++i) {
+      int rc = me_in ? tree_collective(ALLREDUCE, nullptr, nullptr, counts[i], wire, wire, op, chunk_bytes_in[i],
+                                       active, stream)
+                     : skip_op(stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  std::vector<RelayWork> works(n_buckets);
+  int max_lanes = 1;
+  for (int i = 0; i < n_buckets; ++i) {
+    RelayWork& w = works[i];
+    memset(&w, 0, sizeof(w));
+    TreePlan& plan = w.plan;
+    plan.n_trees = nt;
+    plan.do_reduce = 1;
+    plan.do_bcast = 1;
+    long long chunk_bytes = chunk_bytes_in[i];
+    if (tun.tree_chunk_max_bytes >= 16 && chunk_bytes > tun.tree_chunk_max_bytes) chunk_bytes = tun.tree_chunk_max_bytes;
+    if (chunk_bytes < 16) chunk_bytes = 16;
+    plan.chunk_packs = chunk_bytes / 16;
+    for (int t = 0; t < nt; ++t) {
+      TreeRole& tr = plan.role[t];
+      tr.parent = mine[t].parent;
+      tr.flags = mine[t].flags;
+      tr.n_children = (int)mine[t].children.size();
+      for (int k = 0; k < tr.n_children; ++k) tr.children[k] = mine[t].children[k];
+    }
+    const long long n = counts[i];
+    const long long npacks = (n + epp - 1) / epp;
+    const long long per = (npacks + nt - 1) / nt;
+    for (int t = 0; t <= nt; ++t) plan.slice_begin[t] = std::min<long long>((long long)t * per, npacks);
+    const long long items = ((per + plan.chunk_packs - 1) / plan.chunk_packs) * nt;
+    int lanes = (int)std::min<long long>(items, (long long)std::min(tun.tree_blocks, kMaxBlocks) / 2);
+    if (lanes < 1) lanes = 1;
+    w.lanes = lanes;
+    w.n = n;
+    w.scale = (op == AVG && !active.empty()) ? 1.f / (float)active.size() : 1.f;
+    w.skip = n == 0;
+    max_lanes = std::max(max_lanes, lanes);
+  }
+  const size_t bytes = sizeof(RelayWork) * works.size();
+  if (bytes > relay_work_cap_) {
+    if (d_relay_work_) cudaFree(d_relay_work_);
+    CUDA_TRY(cudaMalloc(&d_relay_work_, bytes));
+    relay_work_cap_ = bytes;
+  }
+  // synchronous copy: the descriptor vector lives on this stack frame
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  CUDA_TRY(cudaMemcpy(d_relay_work_, works.data(), bytes, cudaMemcpyHostToDevice));
+  Window win{};
+  for (int r = 0; r < world_; ++r) win.data[r] = (char*)staging_.peers[r];
+  win.mc = (char*)staging_.mc;
+  win.capacity = staging_.size;
+  DevComm dc;
+  if (fill_comm(participants, win, &dc)) return -1;
+  const int kop = (op == MAX) ? MAX : SUM;
+  const int blocks = 2 * max_lanes;
+  const RelayWork* dw = static_cast<const RelayWork*>(d_relay_work_);
+#define RELAY_LAUNCH(W_)                                                                              \
+  do {                                                                                                \
+    if (kop == MAX) tree_relay_persistent_kernel<W_, MAX><<<blocks, kThreads, 0, stream>>>(dc, dw, n_buckets); \
+    else tree_relay_persistent_kernel<W_, SUM><<<blocks, kThreads, 0, stream>>>(dc, dw, n_buckets);   \
+  } while (0)
+  if (wire == F32) RELAY_LAUNCH(float);
+  else if (wire == BF16) RELAY_LAUNCH(__nv_bfloat16);
+  else if (wire == F16) RELAY_LAUNCH(__half);
+  else { set_error("relay: bad wire dtype %d", wire); return -1; }
+#undef RELAY_LAUNCH
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

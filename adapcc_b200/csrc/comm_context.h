@@ -48,6 +48,11 @@ class CommContext {
   int tree_collective(int prim, const void* in, void* out, long long count, int dtype, int wire,
                       int op, long long chunk_bytes, const std::vector<int>& active,
                       cudaStream_t stream);
+  // Relay duty for a whole training step in ONE persistent kernel: bucket i has counts[i] elements
+  // of `wire` dtype and chunk_bytes[i]; this rank must NOT be in `active`. Falls back to per-bucket
+  // launches when a bucket does not fit the staging window.
+  int tree_relay_persistent(int n_buckets, const long long* counts, const long long* chunk_bytes, int wire, int op,
+                            const std::vector<int>& active, cudaStream_t stream);
   int skip_op(cudaStream_t stream);
   // One-CTA device barrier among `active` (orders peer stores before peer loads across kernels).
   int device_barrier(const std::vector<int>& active, cudaStream_t stream);
@@ -83,6 +88,8 @@ class CommContext {
   SymmContext symm_;
   SymmBuffer staging_, heap_, sig_;
   char* d_state_ = nullptr;            // bar_epoch[], ticket, err, seq
+  void* d_relay_work_ = nullptr;       // RelayWork[] scratch of the persistent relay kernel
+  size_t relay_work_cap_ = 0;
   Strategy strategy_;
   int rank_ = 0, world_ = 1, device_ = 0;
   bool inited_ = false;

@@ -118,7 +118,7 @@ __device__ __forceinline__ void block_barrier(const DevComm& c, BarrierState& b)
 // Every kernel ends with this: persist the pair epochs and let the last block to finish
 // advance the context's op sequence number (device-side, so the kernels stay CUDA-graph
 // capturable: no host-computed epoch is baked into the launch).
-__device__ __forceinline__ void finish_op(const DevComm& c, const BarrierState& b) {
+__device__ __forceinline__ void finish_op(const DevComm& c, const BarrierState& b, unsigned advance = 1) {
   if (b.peer >= 0) c.bar_epoch[blockIdx.x * kMaxRanks + b.peer] = b.epoch;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -126,7 +126,7 @@ __device__ __forceinline__ void finish_op(const DevComm& c, const BarrierState& 
     const uint32_t t = atomicAdd(c.ticket, 1u);
     if (t == gridDim.x - 1) {
       *c.ticket = 0;
-      *c.seq = *c.seq + 1;
+      *c.seq = *c.seq + advance;
     }
   }
 }

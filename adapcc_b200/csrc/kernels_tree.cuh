@@ -107,16 +107,16 @@ __device__ __forceinline__ void reduce_chunk(const DevComm& c, const TreeRole& r
 // chunk travels down while later chunks are still being reduced and neither pipeline ever
 // idles waiting for the other phase.
 template <typename U, typename W, int OP>
-__global__ void __launch_bounds__(kThreads, 1)
-tree_collective_kernel(const __grid_constant__ DevComm c, const __grid_constant__ TreePlan plan,
-                       const U* __restrict__ in, U* __restrict__ out, long long n, float scale) {
+__device__ __forceinline__ void tree_collective_body(const DevComm& c, const TreePlan& plan,
+                                                     const U* __restrict__ in, U* __restrict__ out, long long n,
+                                                     float scale, unsigned long long q, BarrierState& epoch,
+                                                     int lanes) {
   constexpr int kEpp = WireTraits<W>::kEpp;
-  BarrierState epoch = barrier_begin(c);
-  const unsigned long long q = *c.seq;
   const bool in_vec = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
   const bool out_vec = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   char* const local = c.data[c.rank];
-  const int half = gridDim.x >> 1;
+  const int half = lanes;                       // CTAs [0, lanes) reduce, [lanes, 2*lanes) broadcast
+  if ((int)blockIdx.x >= 2 * lanes) return;     // persistent relay grids may be wider than this op
   const bool bcast_side = (int)blockIdx.x >= half;
   const int lane = bcast_side ? blockIdx.x - half : blockIdx.x;   // pipeline lane 0..half-1
   unsigned long long* const my_rflag = c.flag[c.rank] + lane;
@@ -217,7 +217,43 @@ tree_collective_kernel(const __grid_constant__ DevComm c, const __grid_constant_
   }
   // windows are reused by the next op: nobody leaves while a peer may still be pulling
   block_barrier(c, epoch);
+}
+
+template <typename U, typename W, int OP>
+__global__ void __launch_bounds__(kThreads, 1)
+tree_collective_kernel(const __grid_constant__ DevComm c, const __grid_constant__ TreePlan plan,
+                       const U* __restrict__ in, U* __restrict__ out, long long n, float scale) {
+  BarrierState epoch = barrier_begin(c);
+  tree_collective_body<U, W, OP>(c, plan, in, out, n, scale, *c.seq, epoch, (int)(gridDim.x >> 1));
   finish_op(c, epoch);
+}
+
+// Persistent relay kernel: ONE launch serves every gradient bucket of a training step on a rank
+// that is not active in it (a straggler). The rank contributes no data; where the strategy routes
+// other ranks' chunks through it, its CTAs pull them from the children's windows, (re-)reduce, and
+// publish them for the parent, bucket after bucket, without the host re-launching anything and
+// without touching the training stream. `work[i]` describes bucket i (same plans the active ranks
+// run, with this rank's relay roles); op sequence numbers advance exactly as if the buckets had
+// been launched one by one, so relays and active ranks stay in step.
+struct RelayWork {
+  TreePlan plan;
+  long long n;
+  float scale;
+  int skip;        // 1: this rank holds no role in this bucket -> only the sequence number moves
+  int lanes;       // pipeline lanes the active ranks use for this bucket (grid = 2 * lanes there)
+};
+
+template <typename W, int OP>
+__global__ void __launch_bounds__(kThreads, 1)
+tree_relay_persistent_kernel(const __grid_constant__ DevComm c, const RelayWork* __restrict__ work, int n_work) {
+  BarrierState epoch = barrier_begin(c);
+  const unsigned long long q0 = *c.seq;
+  for (int i = 0; i < n_work; ++i) {
+    if (work[i].skip) continue;
+    tree_collective_body<W, W, OP>(c, work[i].plan, (const W*)nullptr, (W*)nullptr, work[i].n, work[i].scale,
+                                   q0 + (unsigned long long)i, epoch, work[i].lanes);
+  }
+  finish_op(c, epoch, (unsigned)n_work);
 }
 
 // Keeps a non-participating rank's op sequence number in step with the others.

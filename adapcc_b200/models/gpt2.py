@@ -26,6 +26,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops.layers import FusedLayerNorm, FusedLinear
+
 
 @dataclass
 class GPT2Config:
@@ -48,12 +50,13 @@ class Block(nn.Module):
         super().__init__()
         d = cfg.n_embd
         self.n_head = cfg.n_head
-        self.ln_1 = nn.LayerNorm(d, eps=cfg.layer_norm_epsilon)
-        self.c_attn = nn.Linear(d, 3 * d)
-        self.c_proj = nn.Linear(d, d)
-        self.ln_2 = nn.LayerNorm(d, eps=cfg.layer_norm_epsilon)
-        self.c_fc = nn.Linear(d, 4 * d)
-        self.c_proj2 = nn.Linear(4 * d, d)
+        # fused kernels on CUDA/bf16, stock ATen otherwise (same parameters either way)
+        self.ln_1 = FusedLayerNorm(d, eps=cfg.layer_norm_epsilon)
+        self.c_attn = FusedLinear(d, 3 * d)
+        self.c_proj = FusedLinear(d, d)
+        self.ln_2 = FusedLayerNorm(d, eps=cfg.layer_norm_epsilon)
+        self.c_fc = FusedLinear(d, 4 * d)
+        self.c_proj2 = FusedLinear(4 * d, d)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         B, T, D = x.shape
@@ -118,7 +121,7 @@ class GPT2DoubleHeads(nn.Module):
         self.wte = nn.Embedding(self.padded_vocab, cfg.n_embd)
         self.wpe = nn.Embedding(cfg.n_positions, cfg.n_embd)
         self.h = nn.ModuleList([Block(cfg) for _ in range(cfg.n_layer)])
-        self.ln_f = nn.LayerNorm(cfg.n_embd, eps=cfg.layer_norm_epsilon)
+        self.ln_f = FusedLayerNorm(cfg.n_embd, eps=cfg.layer_norm_epsilon)
         self.mc_head = nn.Linear(cfg.n_embd, 1)           # SequenceSummary(summary_type="cls_index")
         self.apply(self._init)
         for blk in self.h:                                  # GPT-2 residual-projection scaling

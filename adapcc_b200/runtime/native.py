@@ -72,6 +72,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
         lib.adapcc_broadcast.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_int, ip, c_int, c_void_p]
         lib.adapcc_tree_collective.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_int, c_int,
                                                c_int, c_longlong, ip, c_int, c_void_p]
+        lib.adapcc_tree_relay_persistent.argtypes = [c_void_p, c_int, ctypes.POINTER(c_longlong),
+                                                     ctypes.POINTER(c_longlong), c_int, c_int, ip, c_int, c_void_p]
         lib.adapcc_skip_op.argtypes = [c_void_p, c_void_p]
         lib.adapcc_ctx_check.argtypes = [c_void_p, c_void_p]
         lib.adapcc_ctx_host_barrier.argtypes = [c_void_p]
@@ -268,6 +270,16 @@ class NativeComm:
                                                int(chunk_bytes), arr, n, self._stream_ptr(stream)),
                "tree_collective")
         return out
+
+    def tree_relay_persistent(self, counts, chunk_bytes, wire: str = "float32", op: str = "sum", active=None,
+                              stream=None) -> None:
+        """Relay duty for a whole step (all gradient buckets) in one persistent kernel launch."""
+        n = len(counts)
+        c_arr = (c_longlong * max(1, n))(*[int(x) for x in counts])
+        k_arr = (c_longlong * max(1, n))(*[int(x) for x in chunk_bytes])
+        arr, na = self._active(active)
+        _check(self.lib.adapcc_tree_relay_persistent(self.handle, n, c_arr, k_arr, DTYPE_IDS[wire], OP_IDS[op], arr, na,
+                                                     self._stream_ptr(stream)), "tree_relay_persistent")
 
     def skip_op(self, stream=None) -> None:
         _check(self.lib.adapcc_skip_op(self.handle, self._stream_ptr(stream)), "skip_op")
