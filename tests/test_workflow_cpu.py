@@ -1,0 +1,124 @@
+"""Control-plane workflow on CPU/gloo: DETECT -> PROFILE -> SYNTHESIS -> SETUP -> all_reduce ->
+reconstruct_topology -> DDP hook with relay negotiation (coordinator over real gRPC), launcher CLI."""
+import os
+import socket
+import sys
+import tempfile
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, coord_port, tmp, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from types import SimpleNamespace
+
+        from adapcc_b200 import ALLREDUCE
+        from adapcc_b200.adapcc import AdapCC
+        from adapcc_b200.strategy import Strategy
+
+        args = SimpleNamespace(port=5000, strategy_file=os.path.join(tmp, "strategy", "auto.xml"),
+                               logical_graph=os.path.join(tmp, "topology", "logical_graph.xml"), entry_point=6,
+                               parallel_degree=2, profile_freq=2, backend="gloo", work_dir=tmp,
+                               coordinator_port=coord_port, relay_threshold=0.05)
+        os.makedirs(os.path.join(tmp, "strategy"), exist_ok=True)
+        AdapCC.init(args, rank, rank, world)          # detect + profile + synthesise
+        AdapCC.setup(ALLREDUCE)
+        ok = True
+        if rank == 0:
+            ok &= os.path.exists(os.path.join(tmp, "topology", "topo_detect_0.xml"))
+            ok &= os.path.exists(args.logical_graph) and os.path.exists(args.strategy_file)
+            ok &= all(os.path.exists(os.path.join(tmp, "topology", f"topo_profile_{r}")) for r in range(world))
+            Strategy.from_file(args.strategy_file).validate(world)
+        comm = AdapCC.communicator
+        t = torch.full((1000,), float(rank + 1))
+        comm.all_reduce(t, 1000)
+        ok &= bool(torch.allclose(t, torch.full((1000,), world * (world + 1) / 2)))
+        AdapCC.reconstruct_topology(args, ALLREDUCE)   # clear + init + setup again (re-entrant)
+        comm = AdapCC.communicator
+        t = torch.full((77,), 2.0)
+        comm.all_reduce(t, 77, op="avg")
+        ok &= bool(torch.allclose(t, torch.full((77,), 2.0)))
+        # DDP + hook with relay negotiation
+        model = torch.nn.Linear(16, 4)
+        ddp = torch.nn.parallel.DistributedDataParallel(model)
+        ddp.register_comm_hook(state=None, hook=comm.cuda_allreduce_hook)
+        opt = torch.optim.SGD(ddp.parameters(), lr=0.1)
+        for step in range(3):
+            comm.update_relay(step)
+            loss = ddp(torch.randn(8, 16)).pow(2).mean()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+        w = [torch.zeros_like(model.weight) for _ in range(world)]
+        dist.all_gather(w, model.weight.detach())
+        ok &= all(torch.allclose(w[0], x, atol=1e-6) for x in w)        # replicas stayed in sync
+        ok &= len(comm.stats["hook_rpc_s"]) == 3
+        AdapCC.clear(ALLREDUCE)
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_detect_profile_synth_setup_reconstruct_hook_cpu():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with tempfile.TemporaryDirectory() as tmp:
+        port, cport = _free_port(), _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, cport, tmp, q)) for r in range(world)]
+        [p.start() for p in procs]
+        [p.join(180) for p in procs]
+        assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+        res = dict(q.get(timeout=5) for _ in range(world))
+    assert all(res.values()), res
+
+
+def test_launcher_cli_parity(tmp_path, monkeypatch):
+    from adapcc_b200 import launcher
+
+    monkeypatch.chdir(tmp_path)
+    a = launcher.build_parser().parse_args(["--num-process", "8", "--ips", "10.0.0.1:4,10.0.0.2:4", "--master",
+                                            "10.0.0.1", "--exec-file", "train_ddp.py", "--socket_port", "5000",
+                                            "--entry_point", "7", "--strategy_file", "s.xml", "--logical_graph", "g.xml",
+                                            "--parallel_degree", "2", "--profile_freq", "100"])
+    assert launcher.ip_table(launcher.parse_hosts(a.ips)) == ["10.0.0.1"] * 4 + ["10.0.0.2"] * 4
+    cmds = launcher.commands(a)
+    assert [h for h, _ in cmds] == ["10.0.0.1", "10.0.0.2"]
+    flat = " ".join(cmds[1][1])
+    for flag in ("--port=5000", "--entry_point=7", "--strategy_file=s.xml", "--logical_graph=g.xml",
+                 "--parallel_degree=2", "--profile_freq=100", "--node-rank=1", "--nnodes=2"):
+        assert flag in flat
+    assert launcher.main(["--num-process", "2", "--ips", "127.0.0.1:2", "--dry-run"]) == 0
+    assert (tmp_path / "topology" / "ip_table.txt").read_text() == "127.0.0.1\n127.0.0.1\n"
+
+
+def test_gns_and_checkpoint_helpers(tmp_path):
+    from adapcc_b200.utils.checkpoint import State
+    from adapcc_b200.utils.gns import compute_gns
+
+    torch.manual_seed(0)
+    G = torch.randn(1000)
+    small = torch.stack([(G + torch.randn(1000) * 3).pow(2).sum() for _ in range(64)])
+    big = (G + torch.randn(1000) * 3 / 8).pow(2).sum()            # 64x larger batch -> 8x less noise
+    gns, g2, s = compute_gns(small, big, 1, 64)
+    assert 0.3 * 9000 < float(s) < 3 * 9000 and 0.3 * 1000 < float(g2) < 3 * 1000
+    m = torch.nn.Linear(4, 4)
+    st = State(m, torch.optim.SGD(m.parameters(), lr=0.1), epoch=3, step=17)
+    st.save(tmp_path / "ck.pt")
+    m2 = torch.nn.Linear(4, 4)
+    st2 = State(m2, torch.optim.SGD(m2.parameters(), lr=0.1))
+    assert st2.load(tmp_path / "ck.pt") and st2.epoch == 3 and st2.step == 17
+    assert torch.equal(m.weight, m2.weight)
