@@ -179,9 +179,13 @@ int CommContext::pick_algo(int algo, long long wire_bytes, int op, int wire, boo
   }
   if (algo == ONE_SHOT || algo == TWO_SHOT || algo == NVLS) return algo;
   if (algo != AUTO) { set_error("bad algo %d", algo); return -1; }
+  const bool nvls_pref = nvls_ok && wire_bytes >= tun.nvls_min_bytes && world_ >= tun.nvls_min_ranks;
+  // zero-copy tensors never need the staging pass a one-shot would add: measured on 8xB200 the
+  // in-place NVLS / two-shot kernels are at least as fast as one-shot from 1 KB up
+  // (profiles/allreduce_sweep_8xB200.md)
+  if (w.zero_copy) return nvls_pref ? NVLS : TWO_SHOT;
   if (wire_bytes <= tun.one_shot_max_bytes) return ONE_SHOT;
-  if (nvls_ok && wire_bytes >= tun.nvls_min_bytes && world_ >= tun.nvls_min_ranks) return NVLS;
-  return TWO_SHOT;
+  return nvls_pref ? NVLS : TWO_SHOT;
 }
 
 int CommContext::skip_op(cudaStream_t stream) {

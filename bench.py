@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -166,24 +166,57 @@ def main():
         def comm_fn(seg):                           # NCCL baseline on the same engine / buckets
             dist.all_reduce(seg, op=dist.ReduceOp.AVG)
 
-    engine = FlatDataParallel(model, comm, world_size=world, rank=rank, bucket_mb=a.bucket_mb, lr=6.25e-5,
-                              max_norm=1.0, algo=a.algo, comm_fn=comm_fn)
-
     tokens_per_step = a.batch * a.candidates * seq * world
     host = [synthetic_batch(a.batch, a.candidates, seq, cfg.vocab_size, seed=1000 * rank + i, pin=True)
             for i in range(4)]
     dev_batch = {k: v.to(dev) for k, v in host[0].items()}
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-
     use_graph = a.engine == "graph"
-    c_before = lib.adapcc_launch_count()
-    if use_graph:
-        engine.capture(dev_batch, warmup=2)
-        step_dev = lambda: engine._graph.replay()                      # noqa: E731
-        step_e2e = lambda i: engine.step_graph(host[i % len(host)])    # noqa: E731
+    engine = None
+    if a.engine == "ddp":
+        # the reference's integration: torch DDP + communicator.cuda_allreduce_hook (async, side stream);
+        # DDP's gradient buckets are allocated from the symmetric heap -> zero-copy all-reduce
+        from adapcc_b200.parallel.ddp import symmetric_allocations, wrap_ddp
+
+        model = model.bfloat16()
+        if a.impl == "adapcc" and world > 1:
+            ddp = wrap_ddp(model, AdapCC.communicator, local, bucket_cap_mb=int(a.bucket_mb))
+            pool_ctx = lambda: symmetric_allocations(AdapCC.communicator)      # noqa: E731
+        else:
+            import contextlib
+
+            ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], bucket_cap_mb=int(a.bucket_mb),
+                                                            gradient_as_bucket_view=True) if world > 1 else model
+            pool_ctx = contextlib.nullcontext
+        opt = torch.optim.AdamW(ddp.parameters(), lr=6.25e-5, fused=True)
+        it = [0]
+
+        def ddp_step(batch):
+            if a.impl == "adapcc" and world > 1:
+                AdapCC.communicator.update_relay(it[0])
+            with (pool_ctx() if it[0] < 2 else __import__("contextlib").nullcontext()):
+                loss = ddp(**batch)[0]
+                opt.zero_grad(set_to_none=False)
+                loss.backward()
+            torch.nn.utils.clip_grad_norm_(ddp.parameters(), 1.0)
+            opt.step()
+            it[0] += 1
+            return loss.detach()
+
+        step_dev = lambda: ddp_step(dev_batch)                                                   # noqa: E731
+        step_e2e = lambda i: ddp_step({k: v.to(dev, non_blocking=True) for k, v in host[i % len(host)].items()})  # noqa: E731
+        n_buckets, zero_copy = -1, (a.impl == "adapcc" and world > 1)
     else:
-        step_dev = lambda: engine.step(dev_batch)                      # noqa: E731
-        step_e2e = lambda i: engine.step({k: v.to(dev, non_blocking=True) for k, v in host[i % len(host)].items()})  # noqa: E731
+        engine = FlatDataParallel(model, comm, world_size=world, rank=rank, bucket_mb=a.bucket_mb, lr=6.25e-5,
+                                  max_norm=1.0, algo=a.algo, comm_fn=comm_fn)
+        n_buckets, zero_copy = len(engine.buckets), engine.zero_copy
+        if use_graph:
+            engine.capture(dev_batch, warmup=2)
+            step_dev = lambda: engine._graph.replay()                      # noqa: E731
+            step_e2e = lambda i: engine.step_graph(host[i % len(host)])    # noqa: E731
+        else:
+            step_dev = lambda: engine.step(dev_batch)                      # noqa: E731
+            step_e2e = lambda i: engine.step({k: v.to(dev, non_blocking=True) for k, v in host[i % len(host)].items()})  # noqa: E731
 
     def barrier():
         if world > 1:
@@ -211,7 +244,7 @@ def main():
     e1.record()
     barrier()
     launches = lib.adapcc_launch_count() - c0
-    if use_graph:
+    if use_graph and engine is not None:
         launches = engine.native_launches_per_step * a.steps
     ms_dev = max_over_ranks(e0.elapsed_time(e1) / a.steps)
 
@@ -241,8 +274,8 @@ def main():
             "config": {"model": "gpt2-small-double-heads (12L d768 h12 ctx1024 vocab50262, %d params)" % n_params,
                        "global_batch": a.batch * world, "per_gpu_batch": a.batch, "candidates": a.candidates,
                        "seq_len": seq, "parallelism": f"dp{world}", "engine": a.engine, "algo": a.algo,
-                       "optimizer": "adamw+clip1.0 (fused)", "grad_dtype": "bf16", "zero_copy_grads": engine.zero_copy,
-                       "buckets": len(engine.buckets),
+                       "optimizer": "adamw+clip1.0 (fused)", "grad_dtype": "bf16", "zero_copy_grads": zero_copy,
+                       "buckets": n_buckets,
                        "l2": "working set (params+grads+optimizer state ~2 GB/step) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": tokens_per_step / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": last},
