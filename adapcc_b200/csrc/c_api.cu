@@ -109,6 +109,11 @@ int adapcc_broadcast(void* h, void* buf, long long count, int dtype, int root, c
   return static_cast<CommContext*>(h)->broadcast(buf, count, dtype, root, sorted_active(active, n_active),
                                                  (cudaStream_t)stream);
 }
+int adapcc_alltoall(void* h, const void* in, void* out, long long per_peer, int dtype, const int* active, int n_active,
+                    void* stream) {
+  return static_cast<CommContext*>(h)->alltoall(in, out, per_peer, dtype, sorted_active(active, n_active),
+                                                (cudaStream_t)stream);
+}
 int adapcc_tree_collective(void* h, int prim, const void* in, void* out, long long count, int dtype, int wire,
                            int op, long long chunk_bytes, const int* active, int n_active, void* stream) {
   return static_cast<CommContext*>(h)->tree_collective(prim, in, out, count, dtype, wire, op, chunk_bytes,

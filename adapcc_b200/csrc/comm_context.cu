@@ -305,6 +305,41 @@ int CommContext::broadcast(void* buf, long long count, int dtype, int root, cons
   return 0;
 }
 
+int CommContext::alltoall(const void* in, void* out, long long per_peer, int dtype, const std::vector<int>& active,
+                          cudaStream_t stream) {
+  if (!inited_) { set_error("context not initialised"); return -1; }
+  if (in == out) { set_error("alltoall must be out of place"); return -1; }
+  const bool mine = std::find(active.begin(), active.end(), rank_) != active.end();
+  if (!mine || per_peer == 0) return skip_op(stream);
+  const int na = (int)active.size();
+  const size_t esize = dtype_size(dtype);
+  if (na == 1 && !tun.force_kernel) {
+    CUDA_TRY(cudaMemcpyAsync(out, in, (size_t)per_peer * esize, cudaMemcpyDeviceToDevice, stream));
+    return skip_op(stream);
+  }
+  const int epp = epp_of(dtype);
+  const long long ppacks = (per_peer + epp - 1) / epp;
+  if ((size_t)ppacks * 16 * na > staging_.size) {
+    set_error("alltoall: %lld bytes per peer exceed the staging window; raise staging_mb", ppacks * 16);
+    return -1;
+  }
+  Window w{};
+  for (int r = 0; r < world_; ++r) w.data[r] = (char*)staging_.peers[r];
+  w.mc = (char*)staging_.mc;
+  w.capacity = staging_.size;
+  DevComm dc;
+  if (fill_comm(active, w, &dc)) return -1;
+  int blocks = (int)std::min<long long>((ppacks + kThreads - 1) / kThreads, (long long)std::min(tun.max_blocks, kMaxBlocks));
+  if (blocks < 1) blocks = 1;
+  if (dtype == F32) alltoall_kernel<float><<<blocks, kThreads, 0, stream>>>(dc, (const float*)in, (float*)out, per_peer);
+  else if (dtype == BF16) alltoall_kernel<__nv_bfloat16><<<blocks, kThreads, 0, stream>>>(dc, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, per_peer);
+  else if (dtype == F16) alltoall_kernel<__half><<<blocks, kThreads, 0, stream>>>(dc, (const __half*)in, (__half*)out, per_peer);
+  else { set_error("alltoall: bad dtype %d", dtype); return -1; }
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 int CommContext::tree_collective(int prim, const void* in, void* out, long long count, int dtype, int wire,
                                  int op, long long chunk_bytes, const std::vector<int>& active,
                                  cudaStream_t stream) {

@@ -44,6 +44,9 @@ class CommContext {
              int root, const std::vector<int>& active, cudaStream_t stream);
   int broadcast(void* buf, long long count, int dtype, int root, const std::vector<int>& active,
                 cudaStream_t stream);
+  // Dense all-to-all, `per_peer` elements to/from every active rank (in != out).
+  int alltoall(const void* in, void* out, long long per_peer, int dtype, const std::vector<int>& active,
+               cudaStream_t stream);
   // Strategy-driven tree collective (prim = ALLREDUCE / REDUCE / BOARDCAST).
   int tree_collective(int prim, const void* in, void* out, long long count, int dtype, int wire,
                       int op, long long chunk_bytes, const std::vector<int>& active,

@@ -327,4 +327,44 @@ broadcast_direct_kernel(const __grid_constant__ DevComm c, U* __restrict__ buf, 
   finish_op(c, epoch);
 }
 
+
+// ----------------------------------------------------------------------------------
+// all-to-all (equal splits): rank r pushes block p of its input straight into slot r of peer
+// p's window (128-bit NVLink stores), one barrier, local copy-out. The reference declares
+// ALLTOALL=4 but never implements it (adapcc.py:59-61 calls a missing method).
+// ----------------------------------------------------------------------------------
+template <typename U>
+__global__ void __launch_bounds__(kThreads, 1)
+alltoall_kernel(const __grid_constant__ DevComm c, const U* __restrict__ in, U* __restrict__ out,
+                long long per_peer) {
+  constexpr int kEpp = WireTraits<U>::kEpp;
+  BarrierState epoch = barrier_begin(c);
+  const int na = c.n_active, me = c.my_index;
+  const bool in_vec = (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (per_peer % kEpp) == 0;
+  const bool out_vec = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (per_peer % kEpp) == 0;
+  const long long ppacks = (per_peer + kEpp - 1) / kEpp;       // packs per block (padded)
+  const long long stride = (long long)gridDim.x * kThreads;
+  block_barrier(c, epoch);                                     // every window is free again
+  for (int a = 0; a < na; ++a) {
+    int idx = me + a; if (idx >= na) idx -= na;                // stagger destinations
+    char* dst = c.data[c.active_ranks[idx]] + (long long)me * ppacks * 16;
+    const U* src = in + (long long)idx * per_peer;
+    for (long long j = (long long)blockIdx.x * kThreads + threadIdx.x; j < ppacks; j += stride) {
+      float f[kEpp];
+      load_user<U, kEpp>(src, j * kEpp, per_peer, in_vec, f);
+      st16(dst + j * 16, pack<U>(f));
+    }
+  }
+  block_barrier(c, epoch);
+  const char* local = c.data[c.rank];
+  for (int a = 0; a < na; ++a) {
+    for (long long j = (long long)blockIdx.x * kThreads + threadIdx.x; j < ppacks; j += stride) {
+      float f[kEpp];
+      unpack<U>(ld16(local + ((long long)a * ppacks + j) * 16), f);
+      store_user<U, kEpp>(out + (long long)a * per_peer, j * kEpp, per_peer, out_vec, f);
+    }
+  }
+  finish_op(c, epoch);
+}
+
 }  // namespace adapcc

@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "device_prims.cuh"
 
 namespace adapcc {
 
@@ -86,6 +87,81 @@ fused_ce_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restrict_
   }
 }
 
+// v2: the row is staged in shared memory (a 50 304-wide bf16 row is 100 KB; two CTAs fit per SM), so
+// global memory is read once and written once and every logit costs ONE ex2 instead of two: pass 1
+// loads + row max, pass 2 e = exp(x - max) (kept in smem as bf16 — the output precision) + sum,
+// pass 3 gradient = e / sum - onehot. ncu on v1 showed it SFU/ALU-bound (83 % SM, 32 % DRAM).
+__global__ void __launch_bounds__(512)
+fused_ce_smem_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restrict__ labels,
+                     float* __restrict__ row_loss, int vocab, int stride) {
+  extern __shared__ uint4 srow[];
+  const int row = blockIdx.x;
+  __nv_bfloat16* p = logits + (long long)row * stride;
+  const long long label = labels[row];
+  const bool valid = label >= 0 && label < vocab;
+  const int nvec = stride / 8;
+  __shared__ float red[16];
+  __shared__ float bcast[2];
+
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    uint4 q = ld16(reinterpret_cast<const uint4*>(p) + v);
+    srow[v] = q;
+    float x[8];
+    unpack<__nv_bfloat16>(q, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (v * 8 + i < vocab) m = fmaxf(m, x[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mm = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mm = fmaxf(mm, red[w]);
+    bcast[0] = mm;
+  }
+  __syncthreads();
+  m = bcast[0];
+  const float xl = valid ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(srow)[label]) : 0.f;
+  __syncthreads();                       // label logit read before the row turns into exponentials
+
+  float s = 0.f;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float x[8];
+    unpack<__nv_bfloat16>(srow[v], x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      x[i] = (v * 8 + i < vocab) ? __expf(x[i] - m) : 0.f;
+      s += x[i];
+    }
+    srow[v] = pack<__nv_bfloat16>(x);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ss = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) ss += red[w];
+    bcast[1] = ss;
+    row_loss[row] = valid ? (__logf(ss) + m - xl) : 0.f;
+  }
+  __syncthreads();
+  const float inv = valid ? 1.f / bcast[1] : 0.f;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float e[8];
+    unpack<__nv_bfloat16>(srow[v], e);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = v * 8 + i;
+      e[i] = e[i] * inv - ((valid && c == label) ? 1.f : 0.f);
+    }
+    st16(reinterpret_cast<uint4*>(p) + v, pack<__nv_bfloat16>(e));
+  }
+}
+
 }  // namespace adapcc
 
 extern "C" int adapcc_fused_ce(void* logits, const long long* labels, float* row_loss, int rows, int vocab,
@@ -97,7 +173,19 @@ extern "C" int adapcc_fused_ce(void* logits, const long long* labels, float* row
     return -1;
   }
   if (vocab > stride) { set_error("fused_ce: vocab > stride"); return -1; }
-  fused_ce_kernel<<<rows, 512, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)logits, labels, row_loss, vocab, stride);
+  const size_t smem = (size_t)stride * 2;
+  static int smem_ok = -1;
+  if (smem_ok < 0) {
+    smem_ok = cudaFuncSetAttribute(fused_ce_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) ==
+              cudaSuccess;
+    (void)cudaGetLastError();
+  }
+  const char* force = getenv("ADAPCC_CE_V1");
+  if (smem_ok && smem <= 200 * 1024 && !(force && atoi(force)))
+    fused_ce_smem_kernel<<<rows, 512, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)logits, labels, row_loss, vocab,
+                                                                    stride);
+  else
+    fused_ce_kernel<<<rows, 512, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)logits, labels, row_loss, vocab, stride);
   CUDA_TRY(cudaGetLastError());
   count_launch();
   return 0;

@@ -13,8 +13,9 @@ import torch
 @contextlib.contextmanager
 def symmetric_allocations(communicator):
     """Allocations made inside this context (on the communicator's device) come from the symmetric
-    heap. Wrap the ``DistributedDataParallel(...)`` construction AND the first two iterations (DDP
-    rebuilds its buckets once, after the first backward)."""
+    heap. ``wrap_ddp`` uses it around the ``DistributedDataParallel(...)`` construction and
+    ``rebuild_buckets`` around DDP's one-off bucket rebuild; keep it narrow — everything allocated
+    inside (activations included) would land in the heap."""
     native = communicator._ensure_native() if hasattr(communicator, "_ensure_native") else communicator
     if native is None or native.heap_bytes == 0:
         yield None
@@ -36,3 +37,15 @@ def wrap_ddp(model: torch.nn.Module, communicator, local_rank: int, *, bucket_ca
                   bucket_cap_mb=bucket_cap_mb, gradient_as_bucket_view=True, **ddp_kwargs)
     ddp.register_comm_hook(state=None, hook=communicator.cuda_allreduce_hook)
     return ddp
+
+
+def rebuild_buckets(ddp, communicator) -> bool:
+    """DDP re-buckets its gradients once, after the first backward (order of gradient arrival). Call
+    this right after iteration 0 so the NEW buckets are allocated from the symmetric heap too;
+    otherwise the rebuild happens inside the next forward with ordinary memory and the hook falls back
+    to the staged path. Returns True if a rebuild happened."""
+    reducer = getattr(ddp, "reducer", None)
+    if reducer is None:
+        return False
+    with symmetric_allocations(communicator):
+        return bool(reducer._rebuild_buckets())

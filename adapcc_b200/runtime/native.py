@@ -74,6 +74,7 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
                                                c_int, c_longlong, ip, c_int, c_void_p]
         lib.adapcc_tree_relay_persistent.argtypes = [c_void_p, c_int, ctypes.POINTER(c_longlong),
                                                      ctypes.POINTER(c_longlong), c_int, c_int, ip, c_int, c_void_p]
+        lib.adapcc_alltoall.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, ip, c_int, c_void_p]
         lib.adapcc_skip_op.argtypes = [c_void_p, c_void_p]
         lib.adapcc_ctx_check.argtypes = [c_void_p, c_void_p]
         lib.adapcc_ctx_host_barrier.argtypes = [c_void_p]
@@ -269,6 +270,20 @@ class NativeComm:
                                                c_void_p(out.data_ptr()), tensor.numel(), dt, wd, OP_IDS[op],
                                                int(chunk_bytes), arr, n, self._stream_ptr(stream)),
                "tree_collective")
+        return out
+
+    def all_to_all(self, tensor, out=None, active=None, stream=None):
+        """Dense all-to-all of equal splits: block p of ``tensor`` goes to rank p, block r of the result
+        comes from rank r (``torch.distributed.all_to_all_single`` semantics)."""
+        import torch
+
+        arr, n = self._active(active)
+        if tensor.numel() % n:
+            raise NativeError(f"all_to_all: {tensor.numel()} elements do not split over {n} ranks")
+        out = torch.empty_like(tensor) if out is None else out
+        _check(self.lib.adapcc_alltoall(self.handle, c_void_p(tensor.data_ptr()), c_void_p(out.data_ptr()),
+                                        tensor.numel() // n, self._dt(tensor), arr, n, self._stream_ptr(stream)),
+               "all_to_all")
         return out
 
     def tree_relay_persistent(self, counts, chunk_bytes, wire: str = "float32", op: str = "sum", active=None,

@@ -176,30 +176,29 @@ def main():
     if a.engine == "ddp":
         # the reference's integration: torch DDP + communicator.cuda_allreduce_hook (async, side stream);
         # DDP's gradient buckets are allocated from the symmetric heap -> zero-copy all-reduce
-        from adapcc_b200.parallel.ddp import symmetric_allocations, wrap_ddp
+        from adapcc_b200.parallel.ddp import rebuild_buckets, wrap_ddp
 
         model = model.bfloat16()
         if a.impl == "adapcc" and world > 1:
             ddp = wrap_ddp(model, AdapCC.communicator, local, bucket_cap_mb=int(a.bucket_mb))
-            pool_ctx = lambda: symmetric_allocations(AdapCC.communicator)      # noqa: E731
+            rebuild = lambda: rebuild_buckets(ddp, AdapCC.communicator)        # noqa: E731
         else:
-            import contextlib
-
             ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], bucket_cap_mb=int(a.bucket_mb),
                                                             gradient_as_bucket_view=True) if world > 1 else model
-            pool_ctx = contextlib.nullcontext
+            rebuild = lambda: None                                             # noqa: E731
         opt = torch.optim.AdamW(ddp.parameters(), lr=6.25e-5, fused=True)
         it = [0]
 
         def ddp_step(batch):
             if a.impl == "adapcc" and world > 1:
                 AdapCC.communicator.update_relay(it[0])
-            with (pool_ctx() if it[0] < 2 else __import__("contextlib").nullcontext()):
-                loss = ddp(**batch)[0]
-                opt.zero_grad(set_to_none=False)
-                loss.backward()
+            loss = ddp(**batch)[0]
+            opt.zero_grad(set_to_none=False)
+            loss.backward()
             torch.nn.utils.clip_grad_norm_(ddp.parameters(), 1.0)
             opt.step()
+            if it[0] == 0:
+                rebuild()               # DDP's one-off re-bucketing goes into the symmetric heap too
             it[0] += 1
             return loss.detach()
 

@@ -22,7 +22,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from adapcc_b200 import ALLREDUCE  # noqa: E402
 from adapcc_b200.adapcc import AdapCC  # noqa: E402
 from adapcc_b200.models.gpt2 import GPT2Config, GPT2DoubleHeads, synthetic_batch  # noqa: E402
-from adapcc_b200.parallel.ddp import symmetric_allocations, wrap_ddp  # noqa: E402
+from adapcc_b200.parallel.ddp import rebuild_buckets, wrap_ddp  # noqa: E402
 from adapcc_b200.parallel.engine import FlatDataParallel  # noqa: E402
 
 
@@ -77,13 +77,13 @@ def main():
 
         def step(b, _i=[0]):
             comm.update_relay(step=_i[0])
-            ctx = symmetric_allocations(comm) if _i[0] < 2 else _Null()
-            with ctx:
-                loss = ddp(**b, lm_coef=a.lm_coef, mc_coef=a.mc_coef)[0]
-                opt.zero_grad(set_to_none=False)
-                loss.backward()
+            loss = ddp(**b, lm_coef=a.lm_coef, mc_coef=a.mc_coef)[0]
+            opt.zero_grad(set_to_none=False)
+            loss.backward()
             torch.nn.utils.clip_grad_norm_(ddp.parameters(), a.max_norm)
             opt.step()
+            if _i[0] == 0:
+                rebuild_buckets(ddp, comm)
             _i[0] += 1
             return loss.detach()
 
@@ -98,14 +98,6 @@ def main():
     comm.synchronize()
     AdapCC.clear(ALLREDUCE)
     dist.destroy_process_group()
-
-
-class _Null:
-    def __enter__(self):
-        return None
-
-    def __exit__(self, *x):
-        return False
 
 
 if __name__ == "__main__":

@@ -229,6 +229,17 @@ def main():
                 check(f"tree[{sname}] relay mode={mode} active={act}", x, want, torch.float32, None, 2)
             comm.set_tunable("relay_mode", 0)
 
+    # ---- all-to-all (equal splits) ---------------------------------------------------------------
+    for dtype in (torch.float32, torch.bfloat16):
+        for per in (1, 37, 4096 + 3):
+            blocks = torch.stack([torch.full((per,), float(rank * 16 + p)) for p in range(world)]).to(dtype).to(dev)
+            out = comm.all_to_all(blocks.reshape(-1))
+            comm.check()
+            want = torch.stack([torch.full((per,), float(src * 16 + rank)) for src in range(world)]).reshape(-1)
+            check(f"all_to_all {dtype} per={per}", out, want, dtype, None, 1)
+            check(f"all_to_all input intact {dtype} per={per}", blocks.reshape(-1),
+                  torch.stack([torch.full((per,), float(rank * 16 + p)) for p in range(world)]).reshape(-1), dtype, None, 1)
+
     # ---- persistent relay kernel: one launch forwards every bucket of a step ------------------
     if world >= 3:
         comm.load_strategy(strategies["chain2"])

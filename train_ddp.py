@@ -19,7 +19,7 @@ import torch.optim as optim
 
 from adapcc_b200 import ALLREDUCE
 from adapcc_b200.adapcc import AdapCC
-from adapcc_b200.parallel.ddp import symmetric_allocations, wrap_ddp
+from adapcc_b200.parallel.ddp import rebuild_buckets, wrap_ddp
 
 
 def env_int(a, b, d):
@@ -71,27 +71,19 @@ def init_processes(args):
         if i != 0 and AdapCC.profile_freq and i % AdapCC.profile_freq == 0:
             AdapCC.reconstruct_topology(args, ALLREDUCE)
         t0 = time.time()
-        ctx = symmetric_allocations(AdapCC.communicator) if (use_cuda and args.heap_mb > 0 and i < 2) else _null()
-        with ctx:                       # DDP rebuilds its buckets after the first backward
-            outputs = ddp_model(torch.randn(args.batch, *shape, device=dev))
-            labels = torch.randint(0, classes, [args.batch], device=dev)
-            loss = loss_fn(outputs, labels)
-            optimizer.zero_grad()
-            loss.backward()
+        outputs = ddp_model(torch.randn(args.batch, *shape, device=dev))
+        labels = torch.randint(0, classes, [args.batch], device=dev)
+        loss = loss_fn(outputs, labels)
+        optimizer.zero_grad()
+        loss.backward()
         optimizer.step()
+        if i == 0 and use_cuda and args.heap_mb > 0:
+            rebuild_buckets(ddp_model, AdapCC.communicator)   # DDP's one-off re-bucketing, into the heap
         if WORLD_RANK == 0:
             print("======== step %d \t loss %0.3f \t %.1f ms" % (i, loss.item(), (time.time() - t0) * 1e3), flush=True)
     AdapCC.communicator.synchronize()
     AdapCC.clear(ALLREDUCE)
     dist.destroy_process_group()
-
-
-class _null:
-    def __enter__(self):
-        return None
-
-    def __exit__(self, *a):
-        return False
 
 
 if __name__ == "__main__":
