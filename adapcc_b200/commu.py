@@ -83,6 +83,7 @@ class CudaCommu:
         self.staging_bytes = int(_arg(args, "staging_mb", os.environ.get("ADAPCC_STAGING_MB", 256))) << 20
         self.heap_bytes = int(_arg(args, "heap_mb", os.environ.get("ADAPCC_HEAP_MB", 0))) << 20
         self.verbose = bool(int(os.environ.get("ADAPCC_VERBOSE", "0")))
+        self.nvtx = bool(int(os.environ.get("ADAPCC_NVTX", "0")))         # NVTX range per collective
 
         self.active_gpus = list(range(world_size))
         self.chunk_bytes: Optional[int] = None
@@ -449,6 +450,7 @@ class CudaCommu:
         if chunk_bytes is None:
             chunk_bytes = self.chunk_bytes or default_chunk_bytes(size * buffer.element_size())
         self.stats["ops"] += 1
+        self.stats["bytes"] = self.stats.get("bytes", 0) + size * buffer.element_size()
         if not buffer.is_cuda:
             from .strategy.cpu_executor import tree_collective_cpu
 
@@ -460,6 +462,16 @@ class CudaCommu:
         n = self._ensure_native()
         algo = self._resolve_algo(size, buffer.dtype, active)
         wire = self._wire_for(buffer.dtype)
+        if self.nvtx:
+            torch.cuda.nvtx.range_push(f"adapcc.prim{prim}.{algo}.{size * buffer.element_size()}B")
+        try:
+            self._launch(n, prim, flat, algo, wire, chunk_bytes, active, op, root)
+        finally:
+            if self.nvtx:
+                torch.cuda.nvtx.range_pop()
+        return buffer
+
+    def _launch(self, n, prim, flat, algo, wire, chunk_bytes, active, op, root):
         if algo == "tree":
             n.tree_collective(prim, flat, op=op, wire=wire, chunk_bytes=int(chunk_bytes), active=active)
         elif prim == ALLREDUCE:
@@ -468,7 +480,6 @@ class CudaCommu:
             n.reduce(flat, root=(active[0] if root is None else root), op=op, algo=algo, wire=wire, active=active)
         else:
             n.broadcast(flat, root=(active[0] if root is None else root), active=active)
-        return buffer
 
     # @buffer: torch tensor (device or host), @size: number of elements, @chunk_bytes: pipelining
     # granularity in bytes, @active_gpus: world ranks taking part (reference signature).
@@ -523,8 +534,9 @@ class CudaCommu:
                 self.relay_buffer.append(torch.zeros(size, dtype=buffer.dtype, device=buffer.device))
             else:
                 self.relay_buffer.append(None)
-        comm_stream, _ = self._streams()
+        comm_stream, relay_stream = self._streams()
         comm_stream.wait_stream(torch.cuda.current_stream(buffer.device))
+        comm_stream.wait_stream(relay_stream)     # relay duty of earlier steps precedes this step's ops (op sequence)
         with torch.cuda.stream(comm_stream):
             if i_am_active or self.current_step <= 1:
                 self.all_reduce(buffer, size, chunk_bytes, active if self.current_step > 1 else list(range(self.world_size)),
