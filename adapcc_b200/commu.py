@@ -111,8 +111,9 @@ class CudaCommu:
                                                fault_tolerant_time=float(_arg(args, "fault_tolerant_time", 10.0)))
                 self.server = make_server(self.coordinator)
                 self.server.start()
-            self.controller = Controller(self.ip_table[0], self.coordinator_port)
-            self.hooker = Hooker(self.ip_table[0], self.coordinator_port)
+            rpc_timeout = float(_arg(args, "fault_tolerant_time", 10.0)) * 2 + float(_arg(args, "relay_threshold", 0.1)) + 20
+            self.controller = Controller(self.ip_table[0], self.coordinator_port, timeout=rpc_timeout)
+            self.hooker = Hooker(self.ip_table[0], self.coordinator_port, timeout=rpc_timeout)
 
         # ---- controller agent ---------------------------------------------------------------------
         self.step_queue: Queue = Queue()
@@ -264,7 +265,13 @@ class CudaCommu:
     # workflow
     # ==========================================================================================
     def clear(self):
-        """stop the controller and the grpc server"""
+        """stop the controller and the grpc server (collective: a slower rank may still be
+        negotiating its last step, so nobody tears the coordinator down before everyone arrived)"""
+        if self.native is not None:
+            import torch
+
+            torch.cuda.synchronize(self.local_rank)
+        self._barrier()
         self.update_relay(-1)
         if self.controller_thread.is_alive():
             self.controller_thread.join(timeout=5)
@@ -511,7 +518,11 @@ class CudaCommu:
 
         if self.local_hook_num == 0 and self.relay_control:
             t0 = time.time()
-            self.active_gpus = sorted(self.hooker.send_ready_request(self.current_step, self.world_rank))
+            try:
+                self.active_gpus = sorted(self.hooker.send_ready_request(self.current_step, self.world_rank))
+            except Exception as e:  # noqa: BLE001  coordinator unreachable: degrade to a plain all-reduce
+                self._log(f"hook RPC failed ({e}); treating every rank as active")
+                self.active_gpus = list(range(self.world_size))
             self.stats["hook_rpc_s"].append(time.time() - t0)
         self.local_hook_num += 1
         buffer = bucket.buffer()
