@@ -72,6 +72,11 @@ class CudaCommu:
                 topo.write_ip_table(self.ip_table_file, self.ip_table)
         self.dispatcher = Dispatcher(self.ip_table)
         self.single_server = len(set(self.ip_table)) == 1
+        # multi-server jobs: one NVLink domain (symmetric-memory context) per server + an inter-server leg
+        self.node_ranks = [r for r, ip in enumerate(self.ip_table) if ip == self.ip_table[world_rank]]
+        self.local_roots = topo.local_rank0_list(self.ip_table)
+        self.node_index = self.local_roots.index(self.node_ranks[0])
+        self._inter_group = None
 
         # ---- data-plane policy -----------------------------------------------------------------
         self.algo = _arg(args, "algo", os.environ.get("ADAPCC_ALGO", "auto"))
@@ -158,8 +163,13 @@ class CudaCommu:
             from .runtime.rendezvous import unique_name
 
             name = unique_name(f"adapcc-{self.port}-{self.init_count}")
-            self.native = NativeComm(name, self.world_rank, self.world_size, self.local_rank,
-                                     staging_bytes=self.staging_bytes, heap_bytes=self.heap_bytes)
+            if self.single_server:
+                self.native = NativeComm(name, self.world_rank, self.world_size, self.local_rank,
+                                         staging_bytes=self.staging_bytes, heap_bytes=self.heap_bytes)
+            else:   # one context per server: ranks are numbered inside the server
+                self.native = NativeComm(f"{name}-n{self.node_index}", self.node_ranks.index(self.world_rank),
+                                         len(self.node_ranks), self.local_rank, staging_bytes=self.staging_bytes,
+                                         heap_bytes=self.heap_bytes)
             self.native.set_tunable("relay_mode", self.relay_mode)
             self._apply_tunables()
         return self.native
@@ -467,6 +477,9 @@ class CudaCommu:
                                 chunk_bytes=int(chunk_bytes), relay_mode=self.relay_mode)
             return buffer
         n = self._ensure_native()
+        if not self.single_server:
+            self._hierarchical(n, prim, flat, active, op, root)
+            return buffer
         algo = self._resolve_algo(size, buffer.dtype, active)
         wire = self._wire_for(buffer.dtype)
         if self.nvtx:
@@ -477,6 +490,84 @@ class CudaCommu:
             if self.nvtx:
                 torch.cuda.nvtx.range_pop()
         return buffer
+
+    def _inter_server_group(self):
+        import torch.distributed as dist
+
+        if self._inter_group is None:
+            self._inter_group = dist.new_group(ranks=self.local_roots)     # collective over ALL ranks
+        return self._inter_group
+
+    def _hierarchical(self, n, prim, flat, active, op, root):
+        """Multi-server data plane: every server is one NVLink domain handled by our kernels; the
+        local roots meet over the inter-server fabric (torch.distributed / NCCL-IB):
+            all-reduce = reduce to the local root -> inter-server all-reduce of the roots -> local
+            broadcast;  reduce / broadcast analogously. The reference moves inter-server chunks with
+            CUDA-aware MPI point-to-point (/root/reference/csrc/trans.cu:75-99); the strategy's
+            cross-server tree edges collapse onto this two-level scheme."""
+        import torch
+        import torch.distributed as dist
+
+        group = self._inter_server_group()
+        me = self.world_rank
+        local = [self.node_ranks.index(r) for r in active if r in self.node_ranks]
+        all_local = list(range(len(self.node_ranks)))
+        i_am_root = me == self.node_ranks[0]
+        red = "max" if op == "max" else "sum"
+        root = active[0] if root is None else root
+        if prim in (ALLREDUCE, REDUCE):
+            if local and 0 not in local:
+                local_plus = sorted(set(local) | {0})              # the local root always collects
+            else:
+                local_plus = local
+            mine_active = me in active
+            if not mine_active and self.node_ranks.index(me) in local_plus:
+                flat_in = torch.zeros_like(flat) if red == "sum" else torch.full_like(flat, float("-inf"))
+            else:
+                flat_in = flat
+            if local_plus:
+                n.reduce(flat_in, root=0, op=red, algo="auto", active=local_plus)
+            if i_am_root:
+                buf = flat_in if local_plus else (torch.zeros_like(flat) if red == "sum" else torch.full_like(flat, float("-inf")))
+                if prim == ALLREDUCE:
+                    dist.all_reduce(buf, op=dist.ReduceOp.MAX if red == "max" else dist.ReduceOp.SUM, group=group)
+                else:
+                    root_node_root = next(r0 for r0 in self.local_roots if self.ip_table[r0] == self.ip_table[root])
+                    dist.reduce(buf, dst=root_node_root, op=dist.ReduceOp.MAX if red == "max" else dist.ReduceOp.SUM,
+                                group=group)
+                if op == "avg":
+                    buf.mul_(1.0 / max(1, len(active)))
+                if buf is not flat:
+                    flat.copy_(buf) if (mine_active or prim == ALLREDUCE) else None
+                    src_buf = buf
+                else:
+                    src_buf = flat
+            if prim == ALLREDUCE:
+                if not mine_active and not i_am_root:
+                    scratch = torch.empty_like(flat)                # inactive ranks keep their own tensor
+                    n.broadcast(scratch, root=0, active=all_local)
+                elif i_am_root and not mine_active:
+                    n.broadcast(src_buf, root=0, active=all_local)
+                else:
+                    n.broadcast(flat, root=0, active=all_local)
+            elif self.ip_table[root] == self.ip_table[me]:
+                # REDUCE: the result sits on the root's server's local root; hand it to `root` itself
+                r_local = self.node_ranks.index(root)
+                if r_local != 0:
+                    n.broadcast(flat if me == root else (src_buf if i_am_root else torch.empty_like(flat)), root=0,
+                                active=sorted({0, r_local})) if me in (root, self.node_ranks[0]) else n.skip_op()
+        else:   # BOARDCAST
+            root_local_root = next(r0 for r0 in self.local_roots if self.ip_table[r0] == self.ip_table[root])
+            if self.ip_table[root] == self.ip_table[me]:
+                r_local = self.node_ranks.index(root)
+                if r_local != 0:                                     # bring the data to the server's local root
+                    if me in (root, self.node_ranks[0]):
+                        n.broadcast(flat, root=r_local, active=sorted({0, r_local}))
+                    else:
+                        n.skip_op()
+            if i_am_root:
+                dist.broadcast(flat, src=root_local_root, group=group)
+            n.broadcast(flat, root=0, active=all_local)
 
     def _launch(self, n, prim, flat, algo, wire, chunk_bytes, active, op, root):
         if algo == "tree":

@@ -46,6 +46,9 @@ def _worker(rank, world, port, coord_port, tmp, q):
         t = torch.full((1000,), float(rank + 1))
         comm.all_reduce(t, 1000)
         ok &= bool(torch.allclose(t, torch.full((1000,), world * (world + 1) / 2)))
+        a2a = AdapCC.alltoall(torch.arange(world * 3, dtype=torch.float32) + 100 * rank)
+        want = torch.cat([torch.arange(rank * 3, rank * 3 + 3, dtype=torch.float32) + 100 * src for src in range(world)])
+        ok &= bool(torch.equal(a2a, want))
         AdapCC.reconstruct_topology(args, ALLREDUCE)   # clear + init + setup again (re-entrant)
         comm = AdapCC.communicator
         t = torch.full((77,), 2.0)
@@ -103,6 +106,22 @@ def test_launcher_cli_parity(tmp_path, monkeypatch):
         assert flag in flat
     assert launcher.main(["--num-process", "2", "--ips", "127.0.0.1:2", "--dry-run"]) == 0
     assert (tmp_path / "topology" / "ip_table.txt").read_text() == "127.0.0.1\n127.0.0.1\n"
+
+
+def test_fault_injector(monkeypatch):
+    from adapcc_b200.utils.fault import FaultInjector
+
+    monkeypatch.setenv("ADAPCC_STRAGGLERS", "1,3")
+    monkeypatch.setenv("ADAPCC_STRAGGLE_MS", "40")
+    monkeypatch.setenv("ADAPCC_KILL", "2@7")
+    inj = FaultInjector.from_env(3)
+    assert inj.delay_s(0) == 0 and abs(inj.delay_s(2) - 0.04) < 1e-9
+    assert FaultInjector.from_env(0).delay_s(5) == 0
+    assert FaultInjector.from_env(2).kill_at == {2: 7}
+    import time
+    t0 = time.time()
+    inj.before_backward(3)
+    assert time.time() - t0 >= 0.035 and inj.log
 
 
 def test_gns_and_checkpoint_helpers(tmp_path):
