@@ -249,6 +249,17 @@ class CudaCommu:
         import torch
 
         _, relay_stream = self._streams()
+        if not self.single_server:
+            # hierarchical path: every rank of a server takes part in the local legs, so a relay joins
+            # the collective with a scratch buffer (it contributes nothing and discards the result)
+            with torch.cuda.device(self.local_rank), torch.cuda.stream(relay_stream):
+                for i, (numel, chunk_bytes, dtype) in enumerate(self.bucket_info):
+                    if self.relay_buffer[i] is None:
+                        self.relay_buffer[i] = torch.zeros(numel, dtype=dtype, device=f"cuda:{self.local_rank}")
+                    self._collective(ALLREDUCE, self.relay_buffer[i], numel, chunk_bytes, active, self.reduce_op)
+                    self.relay_signal_queue.put(step)
+            relay_stream.synchronize()
+            return
         with torch.cuda.device(self.local_rank), torch.cuda.stream(relay_stream):
             tree = [self._resolve_algo(n, dt, active) == "tree" for n, _, dt in self.bucket_info]
             wires = {self._wire_for(dt) or str(dt).replace("torch.", "") for _, _, dt in self.bucket_info}
@@ -395,7 +406,8 @@ class CudaCommu:
             from .runtime.native import last_error
 
             n = self._ensure_native()
-            F = ctypes.c_float * w
+            nw = n.world                               # ranks of this NVLink domain (== w on one server)
+            F = ctypes.c_float * nw
             lat, rd, wr, nv = F(), F(), F(), ctypes.c_float(0)
             n.lib.adapcc_profile_links.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_int, F, F, F,
                                                    ctypes.POINTER(ctypes.c_float), ctypes.c_void_p]
@@ -405,11 +417,52 @@ class CudaCommu:
                                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
             if rc != 0:
                 raise RuntimeError(f"link profiling failed: {last_error()}")
-            topo.write_profile(path, self.world_rank, w, list(lat), list(rd), list(wr), float(nv.value))
+            glat, grd, gwr = [0.0] * w, [0.0] * w, [0.0] * w
+            members = list(range(w)) if self.single_server else self.node_ranks
+            for j, g in enumerate(members):
+                glat[g], grd[g], gwr[g] = lat[j], rd[j], wr[j]
+            if not self.single_server:
+                self._profile_inter_server(glat, grd)
+            topo.write_profile(path, self.world_rank, w, glat, grd, gwr, float(nv.value))
         else:
             lat = [0.0 if d == self.world_rank else 50.0 for d in range(w)]
             bw = [0.0 if d == self.world_rank else 1.0 for d in range(w)]
             topo.write_profile(path, self.world_rank, w, lat, bw)
+
+    def _profile_inter_server(self, lat_us, bw_gbs, nbytes: int = 16 << 20):
+        """Inter-server probes between the local roots, N-1 rounds like the reference's
+        MPI_Isend/Irecv rounds (/root/reference/csrc/profile.cu:220-334): in round i server s sends to
+        server (s+i)%N and receives from (s-i)%N; bandwidth from one large message, latency from small
+        ping-pongs. Only the local roots measure; their rows carry the server-to-server numbers."""
+        import torch
+        import torch.distributed as dist
+
+        roots = self.local_roots
+        N = len(roots)
+        if self.world_rank not in roots or N < 2:
+            return
+        s = roots.index(self.world_rank)
+        dev = torch.device("cuda", self.local_rank)
+        big = torch.empty(nbytes // 4, device=dev)
+        small = torch.zeros(16, device=dev)
+        for i in range(1, N):
+            dst, src = roots[(s + i) % N], roots[(s - i) % N]
+            for buf, reps, kind in ((small, 20, "lat"), (big, 3, "bw")):
+                for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, buf, dst),
+                                                 dist.P2POp(dist.irecv, torch.empty_like(buf), src)]):
+                    w.wait()                        # warm-up: connection setup is not link latency
+                torch.cuda.synchronize()
+                t0 = time.time()
+                for _ in range(reps):
+                    ops = [dist.P2POp(dist.isend, buf, dst), dist.P2POp(dist.irecv, torch.empty_like(buf), src)]
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
+                torch.cuda.synchronize()
+                dt = (time.time() - t0) / reps
+                if kind == "lat":
+                    lat_us[dst] = dt * 1e6
+                else:
+                    bw_gbs[dst] = buf.numel() * 4 / dt / 1e9
 
     def _gather_topo_profile(self):
         files = [os.path.join(self.topo_dir, f"topo_profile_{r}") for r in range(self.world_size)]
@@ -510,64 +563,71 @@ class CudaCommu:
 
         group = self._inter_server_group()
         me = self.world_rank
-        local = [self.node_ranks.index(r) for r in active if r in self.node_ranks]
+        my_local = self.node_ranks.index(me)
         all_local = list(range(len(self.node_ranks)))
-        i_am_root = me == self.node_ranks[0]
+        i_am_root = my_local == 0
         red = "max" if op == "max" else "sum"
+        rop = dist.ReduceOp.MAX if red == "max" else dist.ReduceOp.SUM
         root = active[0] if root is None else root
-        if prim in (ALLREDUCE, REDUCE):
-            if local and 0 not in local:
-                local_plus = sorted(set(local) | {0})              # the local root always collects
-            else:
-                local_plus = local
-            mine_active = me in active
-            if not mine_active and self.node_ranks.index(me) in local_plus:
-                flat_in = torch.zeros_like(flat) if red == "sum" else torch.full_like(flat, float("-inf"))
-            else:
-                flat_in = flat
-            if local_plus:
-                n.reduce(flat_in, root=0, op=red, algo="auto", active=local_plus)
-            if i_am_root:
-                buf = flat_in if local_plus else (torch.zeros_like(flat) if red == "sum" else torch.full_like(flat, float("-inf")))
-                if prim == ALLREDUCE:
-                    dist.all_reduce(buf, op=dist.ReduceOp.MAX if red == "max" else dist.ReduceOp.SUM, group=group)
-                else:
-                    root_node_root = next(r0 for r0 in self.local_roots if self.ip_table[r0] == self.ip_table[root])
-                    dist.reduce(buf, dst=root_node_root, op=dist.ReduceOp.MAX if red == "max" else dist.ReduceOp.SUM,
-                                group=group)
-                if op == "avg":
-                    buf.mul_(1.0 / max(1, len(active)))
-                if buf is not flat:
-                    flat.copy_(buf) if (mine_active or prim == ALLREDUCE) else None
-                    src_buf = buf
-                else:
-                    src_buf = flat
-            if prim == ALLREDUCE:
-                if not mine_active and not i_am_root:
-                    scratch = torch.empty_like(flat)                # inactive ranks keep their own tensor
-                    n.broadcast(scratch, root=0, active=all_local)
-                elif i_am_root and not mine_active:
-                    n.broadcast(src_buf, root=0, active=all_local)
-                else:
-                    n.broadcast(flat, root=0, active=all_local)
-            elif self.ip_table[root] == self.ip_table[me]:
-                # REDUCE: the result sits on the root's server's local root; hand it to `root` itself
-                r_local = self.node_ranks.index(root)
-                if r_local != 0:
-                    n.broadcast(flat if me == root else (src_buf if i_am_root else torch.empty_like(flat)), root=0,
-                                active=sorted({0, r_local})) if me in (root, self.node_ranks[0]) else n.skip_op()
-        else:   # BOARDCAST
-            root_local_root = next(r0 for r0 in self.local_roots if self.ip_table[r0] == self.ip_table[root])
+        root_node_root = next(r0 for r0 in self.local_roots if self.ip_table[r0] == self.ip_table[root])
+
+        def identity():
+            return torch.zeros_like(flat) if red == "sum" else torch.full_like(flat, float("-inf"))
+
+        if prim == BOARDCAST:
             if self.ip_table[root] == self.ip_table[me]:
                 r_local = self.node_ranks.index(root)
-                if r_local != 0:                                     # bring the data to the server's local root
-                    if me in (root, self.node_ranks[0]):
+                if r_local != 0:                       # bring the data to this server's local root first
+                    if my_local in (0, r_local):
                         n.broadcast(flat, root=r_local, active=sorted({0, r_local}))
                     else:
                         n.skip_op()
             if i_am_root:
-                dist.broadcast(flat, src=root_local_root, group=group)
+                dist.broadcast(flat, src=root_node_root, group=group)
             n.broadcast(flat, root=0, active=all_local)
+            return
+
+        # ---- ALLREDUCE / REDUCE: (1) reduce inside the server to its local root ----------------------
+        mine_active = me in active
+        local = sorted(self.node_ranks.index(r) for r in active if r in self.node_ranks)
+        members = sorted(set(local) | {0}) if local else []
+        keep_own = (not mine_active) or (prim == REDUCE and me != root)   # my tensor must survive untouched
+        work = flat
+        if my_local in members and (not mine_active):
+            work = identity()                           # the collecting root contributes nothing itself
+        elif i_am_root and keep_own:
+            work = flat.clone()
+        if members:
+            n.reduce(work, root=0, op=red, algo="auto", active=members)
+        # ---- (2) the local roots meet over the inter-server fabric -----------------------------------
+        if i_am_root:
+            if not members:
+                work = identity()
+            if prim == ALLREDUCE:
+                dist.all_reduce(work, op=rop, group=group)
+            else:
+                dist.reduce(work, dst=root_node_root, op=rop, group=group)
+            if op == "avg":
+                work.mul_(1.0 / max(1, len(active)))
+        # ---- (3) hand the result out inside the server --------------------------------------------
+        if prim == ALLREDUCE:
+            if i_am_root:
+                n.broadcast(work, root=0, active=all_local)
+                if mine_active and work is not flat:
+                    flat.copy_(work)
+            else:
+                n.broadcast(flat if mine_active else torch.empty_like(flat), root=0, active=all_local)
+        elif self.ip_table[root] == self.ip_table[me]:
+            r_local = self.node_ranks.index(root)
+            if r_local != 0:                            # result is on the local root; `root` wants it
+                if my_local == 0:
+                    n.broadcast(work, root=0, active=sorted({0, r_local}))
+                elif my_local == r_local:
+                    n.broadcast(flat, root=0, active=sorted({0, r_local}))
+                else:
+                    n.skip_op()
+            elif i_am_root and work is not flat:
+                flat.copy_(work)
 
     def _launch(self, n, prim, flat, algo, wire, chunk_bytes, active, op, root):
         if algo == "tree":

@@ -75,6 +75,10 @@ int adapcc_ctx_set_tunable(void* h, int key, long long value) {
     case 6: c->tun.tree_chunk_max_bytes = value; break;
     case 7: c->tun.nvls_min_ranks = (int)value; break;
     case 8: c->tun.force_kernel = (int)value; break;
+    case 9: c->tun.pipe_min_bytes = value; break;
+    case 10: c->tun.pipe_stagers = (int)value; break;
+    case 11: c->tun.pipe_links = (int)value; break;
+    case 12: c->tun.pipe_piece_bytes = value; break;
     default: set_error("unknown tunable %d", key); return -1;
   }
   return 0;

@@ -3,6 +3,7 @@
 #include <algorithm>
 
 #include "kernels_direct.cuh"
+#include "kernels_pipelined.cuh"
 #include "kernels_tree.cuh"
 
 namespace adapcc {
@@ -73,6 +74,25 @@ int launch_direct(int algo, int blocks, cudaStream_t s, const DevComm& dc, const
   if (na <= 8) return launch_direct_nr<U, W, OP, 8>(algo, blocks, s, dc, i, o, n, scale, flags, root);
   return launch_direct_nr<U, W, OP, 16>(algo, blocks, s, dc, i, o, n, scale, flags, root);
 }
+template <typename U, typename W, int OP>
+int launch_pipelined(int algo, int stagers, int links, int pieces, cudaStream_t s, const DevComm& dc, PipeState* ps,
+                     const void* in, void* out, long long n, float scale) {
+  const U* i = static_cast<const U*>(in);
+  U* o = static_cast<U*>(out);
+  const int blocks = stagers + links;
+  const int na = dc.n_active;
+#define PIPE_LAUNCH(ALGO_, NR_) \
+  allreduce_pipelined_kernel<U, W, OP, ALGO_, NR_><<<blocks, kThreads, 0, s>>>(dc, ps, i, o, n, scale, stagers, pieces)
+  if (algo == NVLS) PIPE_LAUNCH(NVLS, 2);
+  else if (na <= 2) PIPE_LAUNCH(TWO_SHOT, 2);
+  else if (na <= 4) PIPE_LAUNCH(TWO_SHOT, 4);
+  else if (na <= 8) PIPE_LAUNCH(TWO_SHOT, 8);
+  else PIPE_LAUNCH(TWO_SHOT, 16);
+#undef PIPE_LAUNCH
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
 }  // namespace
 
 CommContext::~CommContext() { destroy(); }
@@ -91,6 +111,8 @@ int CommContext::init(const std::string& name, int rank, int world, int device, 
   }
   CUDA_TRY(cudaMalloc(&d_state_, kStateBytes));
   CUDA_TRY(cudaMemset(d_state_, 0, kStateBytes));
+  CUDA_TRY(cudaMalloc(&d_pipe_, sizeof(PipeState)));
+  CUDA_TRY(cudaMemset(d_pipe_, 0, sizeof(PipeState)));
   CUDA_TRY(cudaDeviceSynchronize());
   const char* e = getenv("ADAPCC_MAX_BLOCKS");
   if (e && atoi(e) > 0) tun.max_blocks = std::min(atoi(e), kMaxBlocks);
@@ -111,6 +133,8 @@ void CommContext::destroy() {
   symm_.free(&sig_);
   if (d_state_) cudaFree(d_state_);
   d_state_ = nullptr;
+  if (d_pipe_) cudaFree(d_pipe_);
+  d_pipe_ = nullptr;
   if (d_relay_work_) cudaFree(d_relay_work_);
   d_relay_work_ = nullptr;
   relay_work_cap_ = 0;
@@ -221,6 +245,7 @@ int CommContext::reduce(const void* in, void* out, long long count, int dtype, i
   }
   const float scale = (op == AVG) ? 1.f / (float)na : 1.f;
   const int kop = (op == MAX) ? MAX : SUM;
+  const bool root_only_op = root >= 0;
   Window w = resolve(in, out, (size_t)count * esize, dtype == wire);
   int a = pick_algo(algo, count * (long long)wsize, kop, wire, na == world_, w);
   if (a < 0) return -1;
@@ -248,6 +273,22 @@ int CommContext::reduce(const void* in, void* out, long long count, int dtype, i
     const char* pin = (const char*)in + (size_t)done * esize;
     char* pout = (char*)out + (size_t)done * esize;
     if (w.zero_copy && done) { set_error("internal: zero-copy op split into pieces"); return -1; }
+    const long long wire_bytes = n * (long long)wsize;
+    const bool pipelined = !w.zero_copy && !root_only_op && (a == NVLS || a == TWO_SHOT) && tun.pipe_min_bytes > 0 &&
+                           wire_bytes >= tun.pipe_min_bytes &&
+                           tun.pipe_stagers + tun.pipe_links <= kMaxBlocks && tun.pipe_stagers > 0 && tun.pipe_links > 0;
+    if (pipelined) {
+      int pieces = (int)std::min<long long>(kMaxPieces, std::max<long long>(4, (wire_bytes + tun.pipe_piece_bytes - 1) /
+                                                                                  std::max<long long>(1, tun.pipe_piece_bytes)));
+      int rc = ADAPCC_DISPATCH_TYPES(dtype, wire, {
+        if (kop == MAX)
+          return launch_pipelined<U, W, MAX>(a, tun.pipe_stagers, tun.pipe_links, pieces, stream, dc, (PipeState*)d_pipe_, pin, pout, n, scale);
+        return launch_pipelined<U, W, SUM>(a, tun.pipe_stagers, tun.pipe_links, pieces, stream, dc, (PipeState*)d_pipe_, pin, pout, n, scale);
+      });
+      if (rc) return rc;
+      done += n;
+      continue;
+    }
     int rc = ADAPCC_DISPATCH_TYPES(dtype, wire, {
       if (kop == MAX) return launch_direct<U, W, MAX>(a, blocks, stream, dc, pin, pout, n, scale, flags, root_index);
       return launch_direct<U, W, SUM>(a, blocks, stream, dc, pin, pout, n, scale, flags, root_index);

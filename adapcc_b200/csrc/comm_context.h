@@ -21,6 +21,9 @@ struct Tunables {
   int nvls_min_ranks = 3;              // NVLS only pays off when >2 ranks share the switch reduction
   int relay_mode = RELAY_FORWARD;
   long long timeout_ms = 30000;
+  long long pipe_min_bytes = 32ll << 20;   // staged ops at least this large use the pipelined kernel (0 = never)
+  int pipe_stagers = 48, pipe_links = 48;   // CTAs of its two sub-grids
+  long long pipe_piece_bytes = 16ll << 20;
   int force_kernel = 0;                // run kernels even for a single participant (smoke / ncu)
   int tree_blocks = 128;                // CTAs of the tree kernel (half reduce, half broadcast)
   long long tree_chunk_max_bytes = 256 << 10;  // device pipelining granularity (wire bytes)
@@ -91,6 +94,7 @@ class CommContext {
   SymmContext symm_;
   SymmBuffer staging_, heap_, sig_;
   char* d_state_ = nullptr;            // bar_epoch[], ticket, err, seq
+  void* d_pipe_ = nullptr;             // PipeState of the pipelined staged kernel
   void* d_relay_work_ = nullptr;       // RelayWork[] scratch of the persistent relay kernel
   size_t relay_work_cap_ = 0;
   Strategy strategy_;

@@ -27,7 +27,8 @@ enum DirectFlags : int {
 struct Partition {
   long long npacks, pps;
   int nslices;
-  __device__ __forceinline__ long long slice_begin(int s) const { return (long long)s * pps; }
+  long long pack0 = 0;     // first pack of the piece this partition covers (0 = whole message)
+  __device__ __forceinline__ long long slice_begin(int s) const { return pack0 + (long long)s * pps; }
   __device__ __forceinline__ long long slice_count(int s) const {
     long long b = (long long)s * pps;
     long long c = npacks - b;
@@ -35,14 +36,22 @@ struct Partition {
   }
 };
 
+// Every helper below takes a sub-grid view (bid of nb CTAs); the default is the whole grid. The
+// pipelined staged kernel (kernels_pipelined.cuh) runs stagers and link CTAs as two sub-grids.
+struct SubGrid {
+  int bid, nb;
+  __device__ __forceinline__ SubGrid() : bid(blockIdx.x), nb(gridDim.x) {}
+  __device__ __forceinline__ SubGrid(int b, int n) : bid(b), nb(n) {}
+};
+
 template <typename U, typename W>
 __device__ __forceinline__ void stage_in(const Partition& P, const U* __restrict__ in, long long n,
-                                         bool vec_ok, char* __restrict__ local) {
+                                         bool vec_ok, char* __restrict__ local, SubGrid g = SubGrid()) {
   constexpr int kEpp = WireTraits<W>::kEpp;
-  const long long stride = (long long)gridDim.x * kThreads;
+  const long long stride = (long long)g.nb * kThreads;
   for (int s = 0; s < P.nslices; ++s) {
     const long long base = P.slice_begin(s), cnt = P.slice_count(s);
-    for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < cnt; j0 += stride * kUnroll) {
+    for (long long j0 = (long long)g.bid * kThreads + threadIdx.x; j0 < cnt; j0 += stride * kUnroll) {
       float f[kUnroll][kEpp];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
@@ -60,12 +69,13 @@ __device__ __forceinline__ void stage_in(const Partition& P, const U* __restrict
 
 template <typename U, typename W>
 __device__ __forceinline__ void stage_out(const Partition& P, U* __restrict__ out, long long n,
-                                          bool vec_ok, const char* __restrict__ local, float scale) {
+                                          bool vec_ok, const char* __restrict__ local, float scale,
+                                          SubGrid g = SubGrid()) {
   constexpr int kEpp = WireTraits<W>::kEpp;
-  const long long stride = (long long)gridDim.x * kThreads;
+  const long long stride = (long long)g.nb * kThreads;
   for (int s = 0; s < P.nslices; ++s) {
     const long long base = P.slice_begin(s), cnt = P.slice_count(s);
-    for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < cnt; j0 += stride * kUnroll) {
+    for (long long j0 = (long long)g.bid * kThreads + threadIdx.x; j0 < cnt; j0 += stride * kUnroll) {
       uint4 v[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
@@ -138,11 +148,12 @@ __device__ __forceinline__ void one_shot_phase1(const DevComm& c, long long npac
 
 template <typename W, int OP, int NR>
 __device__ __forceinline__ void two_shot_phase1(const DevComm& c, long long base, long long cnt,
-                                                bool zero_copy, float scale, bool root_only, int root) {
+                                                bool zero_copy, float scale, bool root_only, int root,
+                                                SubGrid g = SubGrid()) {
   constexpr int kEpp = WireTraits<W>::kEpp;
   constexpr int UN = 16 / NR;
   const int na = c.n_active, me = c.my_index;
-  const long long stride = (long long)gridDim.x * kThreads;
+  const long long stride = (long long)g.nb * kThreads;
   char* peers[NR];
 #pragma unroll
   for (int a = 0; a < NR; ++a) {
@@ -151,7 +162,7 @@ __device__ __forceinline__ void two_shot_phase1(const DevComm& c, long long base
     peers[a] = a < na ? c.data[c.active_ranks[idx]] : nullptr;
   }
   char* const root_ptr = root_only ? c.data[c.active_ranks[root]] : nullptr;
-  for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < cnt; j0 += stride * UN) {
+  for (long long j0 = (long long)g.bid * kThreads + threadIdx.x; j0 < cnt; j0 += stride * UN) {
     uint4 v[UN][NR];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
@@ -197,12 +208,12 @@ __device__ __forceinline__ void two_shot_phase1(const DevComm& c, long long base
 
 template <typename W, int OP>
 __device__ __forceinline__ void nvls_phase1(const DevComm& c, long long base, long long cnt, bool zero_copy,
-                                            float scale, bool root_only, int root) {
+                                            float scale, bool root_only, int root, SubGrid g = SubGrid()) {
   constexpr int kEpp = WireTraits<W>::kEpp;
   constexpr int UN = 8;
-  const long long stride = (long long)gridDim.x * kThreads;
+  const long long stride = (long long)g.nb * kThreads;
   char* const root_ptr = root_only ? c.data[c.active_ranks[root]] : nullptr;
-  for (long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x; j0 < cnt; j0 += stride * UN) {
+  for (long long j0 = (long long)g.bid * kThreads + threadIdx.x; j0 < cnt; j0 += stride * UN) {
     uint4 v[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {

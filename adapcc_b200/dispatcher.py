@@ -30,6 +30,10 @@ def _local_names() -> set:
 
 class Dispatcher:
     def __init__(self, ip_table: Sequence[str], scp: str = "scp", dry_run: bool = False):
+        # ADAPCC_SHARED_FS=1: every host sees the same directory (one box, NFS, emulated multi-server
+        # runs) -> plain local copies. Also the fallback when no scp binary exists.
+        env = os.environ.get("ADAPCC_SHARED_FS", "auto")
+        self.shared_fs = env == "1" or (env == "auto" and shutil.which(scp) is None)
         self.ip_table = list(ip_table)
         self.ip_dict = {}
         self.scp = scp
@@ -47,7 +51,7 @@ class Dispatcher:
     # -- transport ---------------------------------------------------------------------------
     def _send(self, src_pattern: str, ip: str, dst_path: str) -> None:
         files = glob.glob(src_pattern) or [src_pattern]
-        if ip in _local_names():
+        if self.shared_fs or ip in _local_names():
             for f in files:
                 if not os.path.exists(f):
                     continue

@@ -108,6 +108,21 @@ def main():
         check(f"allreduce auto oop n={n}", y, ref_reduce(world, n, torch.float32, seed, "sum", all_ranks),
               torch.float32, None, world)
         check(f"allreduce auto oop input intact n={n}", x, gen(rank, n, torch.float32, seed), torch.float32, None, 1)
+    # ---- pipelined staged kernel (stager CTAs + link CTAs), forced on mid-size tensors --------------
+    comm.set_tunable("pipe_min_bytes", 1 << 20)
+    comm.set_tunable("pipe_piece_bytes", 1 << 19)
+    for dtype, wire in [(torch.float32, None), (torch.float32, "bfloat16"), (torch.bfloat16, None)]:
+        wire_t = getattr(torch, wire) if wire else None
+        for algo in [a for a in algos if a != "one_shot"]:
+            for n in [(1 << 20) + 3, (5 << 20) + 1]:
+                seed += 1
+                x = gen(rank, n, dtype, seed).to(dev)
+                comm.all_reduce(x, op="avg", algo=algo, wire=wire)
+                comm.check()
+                check(f"pipelined {algo} {dtype} wire={wire} n={n}", x,
+                      ref_reduce(world, n, dtype, seed, "avg", all_ranks, wire_t), dtype, wire_t, world)
+    comm.set_tunable("pipe_min_bytes", 32 << 20)
+    comm.set_tunable("pipe_piece_bytes", 16 << 20)
     # ---- zero-copy (symmetric heap) ----------------------------------------------------
     for dtype in [torch.float32, torch.bfloat16]:
         for algo in [a for a in algos if a != "one_shot"] + ["auto"]:

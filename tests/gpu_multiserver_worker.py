@@ -15,6 +15,7 @@ from adapcc_b200.adapcc import AdapCC  # noqa: E402
 
 
 def main():
+    os.environ.setdefault("ADAPCC_SHARED_FS", "1")      # the two 'servers' are halves of one box
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -26,12 +27,16 @@ def main():
         topo.write_ip_table(os.path.join(work, "topology", "ip_table.txt"), ["10.0.0.1"] * half + ["10.0.0.2"] * (world - half))
     dist.barrier()
     args = SimpleNamespace(port=5000, strategy_file=os.path.join(work, "s.xml"), logical_graph=os.path.join(work, "lg.xml"),
-                           entry_point=-1, parallel_degree=2, profile_freq=0, work_dir=work, relay_control=False,
+                           entry_point=int(os.environ.get("ENTRY_POINT", 7)), parallel_degree=2, profile_freq=0, work_dir=work,
+                           relay_control=False,
                            staging_mb=64)
     AdapCC.init(args, local, rank, world)
     AdapCC.setup(ALLREDUCE)
     comm = AdapCC.communicator
     assert not comm.single_server and len(comm.node_ranks) in (half, world - half)
+    if rank == 0 and os.path.exists(args.strategy_file):
+        print(open(args.strategy_file).read()[:900], flush=True)
+        print(open(os.path.join(work, "topology", "topo_profile_0")).read(), flush=True)
     ok = True
     base = [torch.Generator().manual_seed(100 + r) for r in range(world)]
     data = torch.stack([torch.randn(100_003, generator=g) for g in base])

@@ -92,6 +92,15 @@ def test_collective_kernels_single_gpu_identity(dev, dtype, wire):
             comm.all_reduce(y, op="avg", algo="two_shot", wire=wire)
             comm.check()
             assert torch.equal(y, want)
+        # pipelined staged kernel (two sub-grids) on one GPU
+        comm.set_tunable("pipe_min_bytes", 1 << 16)
+        comm.set_tunable("pipe_piece_bytes", 1 << 16)
+        for algo in ["two_shot"] + (["nvls"] if comm.multicast else []):
+            y = x.clone()
+            comm.all_reduce(y, op="sum", algo=algo, wire=wire)
+            comm.check()
+            assert torch.equal(y, want), ("pipelined", algo)
+        comm.set_tunable("pipe_min_bytes", 32 << 20)
         # zero-copy path on the symmetric heap
         t = comm.symm_empty(70_000, dtype)
         src = torch.randn(70_000, device=dev).to(dtype)
@@ -236,3 +245,30 @@ def test_moe_exchange_single_rank_matches_local_reference(dev):
         assert torch.allclose(ref.gate.weight.grad.float(), moe.gate.weight.grad.float(), atol=5e-2, rtol=5e-2)
     finally:
         comm.close()
+
+
+def test_reference_c_abi_symbols(dev, tmp_path, monkeypatch):
+    """The six symbols of the reference's communicator.so (initThreads / exitThreads / allreduce /
+    reduce / boardcast / updateActive), called through ctypes exactly like its commu.py does."""
+    import ctypes
+
+    from adapcc_b200.runtime.native import load_library
+
+    lib = load_library()
+    for sym in ("initThreads", "exitThreads", "allreduce", "reduce", "boardcast", "updateActive"):
+        assert hasattr(lib, sym)
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    monkeypatch.setenv("ADAPCC_STAGING_MB", "8")
+    sf = tmp_path / "s.xml"
+    sf.write_text("<trees><root id='0' ip='10.0.0.1'/></trees>")
+    lib.initThreads(ctypes.c_int(0), ctypes.c_char_p(str(sf).encode()), ctypes.c_int(5000 + os.getpid() % 1000))
+    t = torch.ones(16, device=dev) * 3
+    active = (ctypes.c_int * 1)(0)
+    lib.allreduce(ctypes.c_void_p(t.data_ptr()), ctypes.c_int(16), ctypes.c_int(8), active, ctypes.c_int(1))
+    assert torch.equal(t.cpu(), torch.full((16,), 3.0))
+    lib.updateActive(ctypes.c_int(0))
+    lib.allreduce(ctypes.c_void_p(t.data_ptr()), ctypes.c_int(16), ctypes.c_int(8), active, ctypes.c_int(1))
+    assert torch.equal(t.cpu(), torch.full((16,), 3.0))
+    lib.exitThreads(ctypes.c_int(0))
