@@ -66,6 +66,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=0, help="CTAs per collective (0 = library default)")
     ap.add_argument("--out", default="")
     ap.add_argument("--no_tree", action="store_true")
+    ap.add_argument("--pipe_sweep", action="store_true", help="stager/link CTA split sensitivity of the staged path")
     a = ap.parse_args()
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -119,6 +120,28 @@ def main():
                 f"{k}={v * 1e6:8.1f}us/{nbytes * factor / v / 1e9:6.1f}" for k, v in row.items()
                 if k not in ("bytes", "best_vs_nccl")) + f"  best/nccl={row['best_vs_nccl']:.2f}x", flush=True)
         del x
+    if a.pipe_sweep:
+        for nbytes in (1 << 28, 1 << 30):
+            if nbytes > max_bytes:
+                continue
+            n = nbytes // esize
+            x = torch.randn(n, device=dev).to(dtype)
+            for st, ln in ((0, 0), (32, 32), (48, 48), (64, 64), (40, 72), (72, 40)):
+                if st == 0:
+                    comm.set_tunable("pipe_min_bytes", 0)
+                else:
+                    comm.set_tunable("pipe_min_bytes", 32 << 20)
+                    comm.set_tunable("pipe_stagers", st)
+                    comm.set_tunable("pipe_links", ln)
+                t = timeit(lambda: comm.all_reduce(x, algo="auto"), 3, dev, side)
+                comm.check()
+                rows.append({"bytes": nbytes, "pipe_stagers": st, "pipe_links": ln, "auto": t})
+                if rank == 0:
+                    print(f"[pipe] {nbytes} B stagers={st} links={ln}: {t * 1e6:9.1f} us {nbytes * factor / t / 1e9:7.1f} GB/s", flush=True)
+            del x
+        comm.set_tunable("pipe_min_bytes", 32 << 20)
+        comm.set_tunable("pipe_stagers", 48)
+        comm.set_tunable("pipe_links", 48)
     if rank == 0 and a.out:
         os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
         with open(a.out, "w") as f:
