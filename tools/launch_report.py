@@ -25,6 +25,7 @@ def main():
     for name, v in last:
         k = re.sub(r"\s+", " ", name)
         k = re.sub(r"^void ", "", k)
+        k = k.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
         k = re.sub(r"\(.*", "", k)
         k = re.sub(r"<.*", "", k)[:80]
         if "adapcc" in name:
