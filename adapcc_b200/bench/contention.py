@@ -9,7 +9,6 @@ when another flow targets the same source GPU (shared egress port) versus a diff
     torchrun --nproc-per-node 4 -m adapcc_b200.bench.contention
 """
 import argparse
-import ctypes
 import os
 
 import torch

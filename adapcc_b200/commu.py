@@ -27,12 +27,11 @@ import os
 import threading
 import time
 from queue import Empty, Queue
-from types import SimpleNamespace
 from typing import List, Optional
 
 from . import topology as topo
-from .constants import (ALLGATHER, ALLREDUCE, ALLTOALL, BOARDCAST, DETECT, PROFILE, REDUCE, REDUCESCATTER,
-                        RELAY_BYPASS, RELAY_FORWARD)
+from .constants import (ALLGATHER, ALLREDUCE, ALLTOALL, BOARDCAST, DETECT, PROFILE, REDUCE,  # noqa: F401
+                        REDUCESCATTER, RELAY_BYPASS, RELAY_FORWARD)
 from .coord import Controller, Coordinator, Hooker, make_server
 from .dispatcher import Dispatcher
 from .strategy import Strategy, default_chunk_bytes

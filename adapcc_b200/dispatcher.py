@@ -12,7 +12,7 @@ import os
 import shutil
 import socket
 import subprocess
-from typing import Iterable, List, Sequence
+from typing import List, Sequence
 
 _LOCAL = {"127.0.0.1", "localhost", "::1", ""}
 

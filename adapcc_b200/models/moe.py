@@ -16,8 +16,6 @@ parameters are rank-local in expert-parallel mode (fastmoe's ``dp_comm="none"``)
 from __future__ import annotations
 
 import math
-from typing import Optional
-
 import torch
 import torch.nn as nn
 import torch.nn.functional as F

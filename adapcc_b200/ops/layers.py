@@ -8,7 +8,6 @@
 """
 from __future__ import annotations
 
-import ctypes
 from ctypes import c_float, c_int, c_void_p
 
 import torch

@@ -5,8 +5,6 @@ symmetric heap, so the hook's all-reduce touches them in place over NVLink."""
 from __future__ import annotations
 
 import contextlib
-from typing import Optional
-
 import torch
 
 

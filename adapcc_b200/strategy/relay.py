@@ -16,7 +16,7 @@ Golden rows from the reference's logs (tree 0<-1<-{2,3}):
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Iterable, List, Sequence, Set
+from typing import Iterable, List, Set
 
 from ..constants import (ALLREDUCE, BOARDCAST, REDUCE, RELAY_BYPASS, RELAY_FORWARD, TR_HAS_LOCAL,
                          TR_IN_BCAST, TR_IN_REDUCE, TR_PARENT_IS_ROOT, TR_PUBLISH, TR_WANT_RESULT)

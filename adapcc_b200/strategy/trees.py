@@ -12,7 +12,7 @@ rank set, needed for BASELINE config 1: strategy/4.xml at world_size=2) and of i
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Callable, Dict, Iterable, List, Optional, Sequence
+from typing import Callable, Dict, List, Optional, Sequence
 
 from . import xmlio
 

@@ -6,11 +6,11 @@ fastest). ``generate_strategy`` writes the strategy XML and returns the chunk si
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import List, Optional
 
 from ..strategy.trees import Strategy, make_strategy
 from .cost_model import LinkModel, best_chunk_bytes, strategy_time
-from .partrees import DEFAULT_CHUNK, ParTrees
+from .partrees import ParTrees
 from .solver import Solver, SolverError
 
 

@@ -14,7 +14,7 @@ import random
 import sys
 import time
 from dataclasses import dataclass, field
-from typing import Dict, Optional, Set
+from typing import Dict, Set
 
 
 @dataclass

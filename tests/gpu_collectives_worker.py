@@ -9,7 +9,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 import torch
 import torch.distributed as dist

@@ -5,7 +5,6 @@ import os
 import sys
 import tempfile
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -22,7 +21,7 @@ def _worker(rank, world, port, xml, tmp, result_q):
     try:
         from types import SimpleNamespace
 
-        from adapcc_b200 import ALLREDUCE, BOARDCAST, REDUCE
+        from adapcc_b200 import ALLREDUCE
         from adapcc_b200.adapcc import AdapCC
 
         sf = os.path.join(tmp, "strategy.xml")

@@ -88,3 +88,17 @@ def test_cost_model_orders_algorithms():
     deep = strategy_time(make_strategy(8, 1, "chain"), lm, 1 << 26, 1 << 20)
     wide = strategy_time(make_strategy(8, 4, "binary"), lm, 1 << 26, 1 << 20)
     assert wide < deep
+
+
+def test_multiround_broadcast_milp():
+    pytest.importorskip("scipy")
+    from adapcc_b200.synth.multiround import full_arcs, ring_arcs, schedule_broadcast, to_strategy
+
+    rounds = schedule_broadcast(4, ring_arcs(4), root=0, partitions=2)
+    assert len(rounds) == 2                                   # bidirectional ring of 4, 2 partitions: 2 rounds
+    for moves in rounds:                                      # one partition per link per round
+        assert len({(u, v) for u, v, _ in moves}) == len(moves)
+    s = to_strategy(4, rounds, 0, 2)
+    s.validate(4)
+    assert len(s.trees) == 2 and all(t.root == 0 for t in s.trees)
+    assert len(schedule_broadcast(8, full_arcs(8), root=3, partitions=1)) == 1    # one hop on a full mesh

@@ -1,5 +1,3 @@
-import os
-
 from adapcc_b200 import topology as topo
 from adapcc_b200.strategy import xmlio
 

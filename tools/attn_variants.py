@@ -1,7 +1,6 @@
 """Micro-experiment (1 GPU): fwd+bwd time of one GPT-2 block for different QKV layouts."""
 import os
 import sys
-import time
 
 import torch
 import torch.nn as nn
