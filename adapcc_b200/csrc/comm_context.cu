@@ -274,7 +274,11 @@ int CommContext::reduce(const void* in, void* out, long long count, int dtype, i
     char* pout = (char*)out + (size_t)done * esize;
     if (w.zero_copy && done) { set_error("internal: zero-copy op split into pieces"); return -1; }
     const long long wire_bytes = n * (long long)wsize;
-    const bool pipelined = !w.zero_copy && !root_only_op && (a == NVLS || a == TWO_SHOT) && tun.pipe_min_bytes > 0 &&
+    // measured on 8xB200 (profiles/allreduce_sweep_8xB200.md): splitting the grid into stager and link
+    // CTAs helps the staged two-shot (+14 % at 1 GiB, +15 % at n=2) but not staged NVLS, which is bound
+    // by local HBM traffic (6 bytes moved per payload byte), so NVLS opts in only when asked to
+    const bool pipe_algo = a == TWO_SHOT || (a == NVLS && tun.pipe_nvls);
+    const bool pipelined = !w.zero_copy && !root_only_op && pipe_algo && tun.pipe_min_bytes > 0 &&
                            wire_bytes >= tun.pipe_min_bytes &&
                            tun.pipe_stagers + tun.pipe_links <= kMaxBlocks && tun.pipe_stagers > 0 && tun.pipe_links > 0;
     if (pipelined) {

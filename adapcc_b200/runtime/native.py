@@ -102,7 +102,7 @@ def _int_array(values: Sequence[int]):
 
 TUNABLE_KEYS = {"max_blocks": 0, "one_shot_max_bytes": 1, "nvls_min_bytes": 2, "relay_mode": 3,
                 "timeout_ms": 4, "tree_blocks": 5, "tree_chunk_max_bytes": 6, "nvls_min_ranks": 7, "force_kernel": 8, "pipe_min_bytes": 9, "pipe_stagers": 10,
-                "pipe_links": 11, "pipe_piece_bytes": 12}
+                "pipe_links": 11, "pipe_piece_bytes": 12, "pipe_nvls": 13}
 
 
 class _CudaArray:

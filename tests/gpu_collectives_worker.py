@@ -109,6 +109,7 @@ def main():
         check(f"allreduce auto oop input intact n={n}", x, gen(rank, n, torch.float32, seed), torch.float32, None, 1)
     # ---- pipelined staged kernel (stager CTAs + link CTAs), forced on mid-size tensors --------------
     comm.set_tunable("pipe_min_bytes", 1 << 20)
+    comm.set_tunable("pipe_nvls", 1)
     comm.set_tunable("pipe_piece_bytes", 1 << 19)
     for dtype, wire in [(torch.float32, None), (torch.float32, "bfloat16"), (torch.bfloat16, None)]:
         wire_t = getattr(torch, wire) if wire else None

@@ -94,6 +94,7 @@ def test_collective_kernels_single_gpu_identity(dev, dtype, wire):
             assert torch.equal(y, want)
         # pipelined staged kernel (two sub-grids) on one GPU
         comm.set_tunable("pipe_min_bytes", 1 << 16)
+        comm.set_tunable("pipe_nvls", 1)
         comm.set_tunable("pipe_piece_bytes", 1 << 16)
         for algo in ["two_shot"] + (["nvls"] if comm.multicast else []):
             y = x.clone()
