@@ -55,7 +55,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index: int):
-        self.idx, self.proc, self.lines = device_index, None, []
+        self.idx, self.proc, self.lines, self.begin = device_index, None, [], 0
+
+    def mark_begin(self):
+        """Samples from here on count (nvidia-smi needs ~1 s to start on an 8-GPU box, so the
+        process is launched long before the timed region and earlier lines are discarded)."""
+        self.begin = len(self.lines)
 
     def start(self):
         try:
@@ -63,8 +68,15 @@ class ClockSampler:
                                           "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            import atexit
+
+            atexit.register(self._kill)             # never leave a sampler behind if the bench dies
         except OSError:
             self.proc = None
+
+    def _kill(self):
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.kill()
 
     def _pump(self):
         for ln in self.proc.stdout:
@@ -80,7 +92,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.begin:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -140,6 +152,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     lib = load_library()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
 
     cfg = GPT2Config.tiny() if a.tiny else GPT2Config()
     seq = min(a.seq, cfg.n_positions)
@@ -230,11 +245,10 @@ def main():
         return float(t.item())
 
     # ---- (1) device-timed: K steps, inputs resident, CUDA events, max over ranks -------------------
+    sampler.mark_begin()                          # warm-up + both timed loops run the same loaded workload
     for _ in range(max(3, a.warmup)):
         step_dev()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     c0 = lib.adapcc_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -260,7 +274,7 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3) / a.steps)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else {}
 
     if comm is not None:
         AdapCC.communicator.synchronize()
