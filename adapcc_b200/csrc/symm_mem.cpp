@@ -65,7 +65,8 @@ int SymmContext::alloc(size_t bytes, bool want_mc, SymmBuffer* out) {
   *out = SymmBuffer();
   if (bytes == 0) { set_error("symm alloc of 0 bytes"); return -1; }
   if (vmm_ok_) {
-    int rc = alloc_vmm(bytes, want_mc && mc_ok_, out);
+    // a multicast object needs >= 2 devices (cuMulticastCreate rejects numDevices = 1)
+    int rc = alloc_vmm(bytes, want_mc && mc_ok_ && world_ > 1, out);
     if (rc == 0) return 0;
     // alloc_vmm only fails collectively (all ranks agree) before any mapping is kept.
     ADAPCC_LOG(1, "rank %d: VMM symmetric alloc failed (%s); falling back to cudaIpc", rank_,
