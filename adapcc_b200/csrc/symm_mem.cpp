@@ -46,12 +46,8 @@ int SymmContext::init(const std::string& name, int rank, int world, int device) 
   if (e && std::string(e) == "ipc") vmm = mc = false;
   const char* m = getenv("ADAPCC_DISABLE_MULTICAST");
   if (m && atoi(m)) mc = false;
-  // P2P reachability to every peer (one NVLink domain assumed; fail loudly otherwise).
-  for (int p = 0; p < world; ++p) {
-    // ranks map to devices through the launcher; peer device ids are not known here for
-    // multi-process jobs, so reachability is verified when the mapping is established.
-    (void)p;
-  }
+  // P2P reachability is established (or fails loudly) when the peers' allocations are mapped below:
+  // cuMemSetAccess / cudaIpcOpenMemHandle reject devices outside the NVLink / PCIe P2P domain.
   vmm_ok_ = all_agree(vmm);
   mc_ok_ = vmm_ok_ && all_agree(mc);
   ADAPCC_LOG(1, "rank %d/%d dev %d: vmm=%d multicast=%d", rank, world, device, (int)vmm_ok_,

@@ -109,14 +109,33 @@ class Strategy:
             return cls.from_xml(f.read(), world)
 
     # ---- writing -------------------------------------------------------------------------
-    def to_xml(self) -> str:
-        doc = xmlio.Node("trees", dict(self.attrs))
-        doc.children = [t.to_node() for t in self.trees]
-        return xmlio.dumps(doc)
+    def to_xml(self, compact: bool = False) -> str:
+        """``compact=True``: one transmission tree per line with a describing comment (what the shipped
+        sample strategies use); default: indented, one element per line."""
+        if not compact:
+            doc = xmlio.Node("trees", dict(self.attrs))
+            doc.children = [t.to_node() for t in self.trees]
+            return xmlio.dumps(doc)
 
-    def save(self, path) -> None:
+        def rec(t: Tree, x: int, tag: str) -> str:
+            a = f'ip="{t.ip.get(x, "")}" id="{x}"'
+            kids = t.kids(x)
+            if not kids:
+                return f"<{tag} {a}/>"
+            return f"<{tag} {a}>" + "".join(rec(t, c, "gpu") for c in kids) + f"</{tag}>"
+
+        attrs = "".join(f' {k}="{v}"' for k, v in self.attrs.items())
+        out = ['<?xml version="1.0" encoding="utf-8"?>', f"<trees{attrs}>"]
+        for i, t in enumerate(self.trees):
+            out.append(f"  <!-- tree {i}: slice {i} of the tensor, root rank {t.root}, depth {t.depth()}, "
+                       f"{len(t.nodes)} ranks -->")
+            out.append("  " + rec(t, t.root, "root"))
+        out.append("</trees>")
+        return "\n".join(out) + "\n"
+
+    def save(self, path, compact: bool = False) -> None:
         with open(path, "w") as f:
-            f.write(self.to_xml())
+            f.write(self.to_xml(compact))
 
     # ---- queries -------------------------------------------------------------------------
     def ranks(self) -> List[int]:

@@ -15,7 +15,7 @@ from adapcc_b200.topology import local_rank0_list  # noqa: E402
 def ips_for(shape):
     out = []
     for s, n in enumerate(shape):
-        out += [f"10.0.0.{s + 1}"] * n
+        out += [f"node{s + 1}"] * n
     return out
 
 
@@ -36,28 +36,27 @@ def main():
         for intra, suffix in variants:
             s = ParTrees(intra).build(ips, local_rank0_list(ips), 4, bw, lat)
             s.attrs["chunk"] = str(4 << 20)
-            s.save(os.path.join(ROOT, "strategy", f"{name}{suffix}.xml"))
+            s.save(os.path.join(ROOT, "strategy", f"{name}{suffix}.xml"), compact=True)
         if len(ips) <= 8:
             try:
                 m = Solver(time_limit_s=5).solve(min(4, len(ips)), 100e6, bw, lat, ips)
                 m.attrs["chunk"] = str(1 << 20)
-                m.save(os.path.join(ROOT, "strategy", f"{name}_milp.xml"))
+                m.save(os.path.join(ROOT, "strategy", f"{name}_milp.xml"), compact=True)
             except Exception as e:  # noqa: BLE001
                 print("milp skipped for", name, e)
-        # logical graph sample
-        g = xmlio.Node("graph", {"version": "adapcc-b200"})
+        # logical graph sample: one server per line (<graph><server><nic><gpu/>... schema)
+        lines = ['<?xml version="1.0" encoding="utf-8"?>', f'<graph version="adapcc-b200" shape="{name}">']
         r = 0
         for sid, n in enumerate(shape):
-            srv = xmlio.Node("server", {"id": str(sid), "ip": f"10.0.0.{sid + 1}"})
-            nic = xmlio.Node("nic", {"id": "0"})
-            for _ in range(n):
-                nic.children.append(xmlio.Node("gpu", {"id": str(r)}))
-                r += 1
-            srv.children.append(nic)
-            g.children.append(srv)
-        xmlio.dump_file(g, os.path.join(ROOT, "topology", f"logical_graph_{name}.xml"))
+            gpus = "".join(f'<gpu id="{r + i}"/>' for i in range(n))
+            lines.append(f'  <!-- server {sid}: world ranks {r}..{r + n - 1}, one NVLink/NVSwitch domain -->')
+            lines.append(f'  <server ip="node{sid + 1}" id="{sid}" gpus="{n}"><nic id="0">{gpus}</nic></server>')
+            r += n
+        lines.append("</graph>")
+        with open(os.path.join(ROOT, "topology", f"logical_graph_{name}.xml"), "w") as f:
+            f.write("\n".join(lines) + "\n")
     # the tree of the reference's golden logs (0 <- 1 <- {2, 3}) as the default test strategy
-    make_strategy(4, 2, "binary", ips_for([4])).save(os.path.join(ROOT, "strategy", "strategy_test.xml"))
+    make_strategy(4, 2, "binary", ips_for([4])).save(os.path.join(ROOT, "strategy", "strategy_test.xml"), compact=True)
     with open(os.path.join(ROOT, "topology", "ip_table_example.txt"), "w") as f:
         f.write("".join(ip + "\n" for ip in ips_for([4, 4])))
 
