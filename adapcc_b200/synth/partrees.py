@@ -143,5 +143,5 @@ class ParTrees:
         s.attrs["chunk"] = str(chunk)
         s.attrs["prim"] = str(prim)
         if strategy_file:
-            s.save(strategy_file)
+            s.save(strategy_file, compact=True)
         return chunk

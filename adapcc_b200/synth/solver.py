@@ -178,5 +178,5 @@ class Solver:
         s.attrs.update({"prim": str(prim), "chunk": str(chunk),
                         "est_us": f"{strategy_time(s, lm, total, chunk) * 1e6:.1f}"})
         if strategy_file:
-            s.save(strategy_file)
+            s.save(strategy_file, compact=True)
         return chunk

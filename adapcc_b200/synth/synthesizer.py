@@ -106,6 +106,6 @@ class Synthesizer:
         self.last_report["chosen"] = best
         s = cands[best]
         s.attrs.update({"policy": best, "chunk": str(scored[best][1]), "prim": str(prim)})
-        s.save(self.strategy_file)
+        s.save(self.strategy_file, compact=True)
         self.last_strategy = s
         return scored[best][1]
