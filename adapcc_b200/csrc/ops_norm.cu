@@ -25,19 +25,23 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// lane l owns vectors l, l+32, ... (VPL of them), each 8 bf16
-template <int VPL>
-__global__ void __launch_bounds__(kLnWarps * 32)
-ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
-              const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
+// lane l owns vectors l, l+32, ... (VPL of them), each 8 bf16.
+// RES: the row is x + res (the transformer's residual add); the bf16-rounded sum is written to
+// `sum_out` (the new residual stream) and normalised in the same pass, so the separate add kernel
+// and its re-read disappear.
+template <int VPL, bool RES>
+__global__ void __launch_bounds__(kLnWarps * 32, VPL <= 3 ? 3 : 2)
+ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+              const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+              __nv_bfloat16* __restrict__ sum_out, __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
               float* __restrict__ rstd, int rows, float eps) {
   constexpr int D = VPL * 256;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float g[VPL][8], b[VPL][8];
+  uint4 gp[VPL], bp[VPL];                       // packed; unpacked at use (registers buy occupancy here)
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
-    unpack<__nv_bfloat16>(reinterpret_cast<const uint4*>(gamma)[lane + 32 * v], g[v]);
-    unpack<__nv_bfloat16>(reinterpret_cast<const uint4*>(beta)[lane + 32 * v], b[v]);
+    gp[v] = reinterpret_cast<const uint4*>(gamma)[lane + 32 * v];
+    bp[v] = reinterpret_cast<const uint4*>(beta)[lane + 32 * v];
   }
   for (int r = blockIdx.x * kLnWarps + warp; r < rows; r += gridDim.x * kLnWarps) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)r * D);
@@ -46,6 +50,15 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
       unpack<__nv_bfloat16>(ld16(xr + lane + 32 * v), f[v]);
+      if constexpr (RES) {
+        float fr[8];
+        unpack<__nv_bfloat16>(ld16(reinterpret_cast<const uint4*>(res + (size_t)r * D) + lane + 32 * v), fr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[v][i] += fr[i];
+        const uint4 packed = pack<__nv_bfloat16>(f[v]);      // statistics are taken of the ROUNDED sum,
+        st16(reinterpret_cast<uint4*>(sum_out + (size_t)r * D) + lane + 32 * v, packed);
+        unpack<__nv_bfloat16>(packed, f[v]);                 // exactly what add-then-LayerNorm would see
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) s += f[v][i];
     }
@@ -59,27 +72,33 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
     uint4* yr = reinterpret_cast<uint4*>(y + (size_t)r * D);
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-      float o[8];
+      float o[8], g[8], b[8];
+      unpack<__nv_bfloat16>(gp[v], g);
+      unpack<__nv_bfloat16>(bp[v], b);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = (f[v][i] - mu) * rs * g[v][i] + b[v][i];
+      for (int i = 0; i < 8; ++i) o[i] = (f[v][i] - mu) * rs * g[i] + b[i];
       st16(yr + lane + 32 * v, pack<__nv_bfloat16>(o));
     }
     if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
   }
 }
 
-template <int VPL>
-__global__ void __launch_bounds__(kLnWarps * 32)
+// RES: dx += dres (the gradient arriving on the residual stream), fused into the same pass.
+template <int VPL, bool RES>
+__global__ void __launch_bounds__(kLnWarps * 32, VPL <= 3 ? 2 : 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
-              __nv_bfloat16* __restrict__ dx, float* __restrict__ part_dgamma, float* __restrict__ part_dbeta,
-              int rows) {
+              const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
+              float* __restrict__ part_dgamma, float* __restrict__ part_dbeta, int rows) {
   constexpr int D = VPL * 256;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float g[VPL][8], dg[VPL][8], db[VPL][8];
+  // gamma stays packed (bf16x8 per register quad) and is unpacked at use: 12 instead of 24 registers
+  // at D = 768, which is what lets two CTAs (16 rows in flight) share an SM
+  uint4 gp[VPL];
+  float dg[VPL][8], db[VPL][8];
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
-    unpack<__nv_bfloat16>(reinterpret_cast<const uint4*>(gamma)[lane + 32 * v], g[v]);
+    gp[v] = reinterpret_cast<const uint4*>(gamma)[lane + 32 * v];
 #pragma unroll
     for (int i = 0; i < 8; ++i) dg[v][i] = db[v][i] = 0.f;
   }
@@ -91,13 +110,14 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-      float fx[8], fd[8];
+      float fx[8], fd[8], g[8];
       unpack<__nv_bfloat16>(ld16(xr + lane + 32 * v), fx);
       unpack<__nv_bfloat16>(ld16(dr + lane + 32 * v), fd);
+      unpack<__nv_bfloat16>(gp[v], g);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         xh[v][i] = (fx[i] - mu) * rs;
-        gy[v][i] = fd[i] * g[v][i];
+        gy[v][i] = fd[i] * g[i];
         c1 += gy[v][i];
         c2 += gy[v][i] * xh[v][i];
         dg[v][i] += fd[i] * xh[v][i];
@@ -112,6 +132,12 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
       float o[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = rs * (gy[v][i] - c1 - xh[v][i] * c2);
+      if constexpr (RES) {
+        float fr[8];
+        unpack<__nv_bfloat16>(ld16(reinterpret_cast<const uint4*>(dres + (size_t)r * D) + lane + 32 * v), fr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += fr[i];
+      }
       st16(ox + lane + 32 * v, pack<__nv_bfloat16>(o));
     }
   }
@@ -143,6 +169,29 @@ template <typename O>
 __global__ void __launch_bounds__(1024)
 colsum_finalize_kernel(const float* __restrict__ part, int nparts, int cols, O* __restrict__ out) {
   __shared__ float sm[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < cols)
+    for (int p = threadIdx.y; p < nparts; p += 32) s += part[(size_t)p * cols + c];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += sm[r][threadIdx.x];
+    out[c] = from_float<O>(t);
+  }
+}
+
+// Two independent reductions of the same shape in one launch (LayerNorm's dgamma and dbeta):
+// blockIdx.y picks the pair. These kernels are ~2.5 us of pure launch latency each, 50 per GPT-2 step.
+template <typename O>
+__global__ void __launch_bounds__(1024)
+colsum_finalize_pair_kernel(const float* __restrict__ part_a, const float* __restrict__ part_b, int nparts, int cols,
+                            O* __restrict__ out_a, O* __restrict__ out_b) {
+  __shared__ float sm[32][33];
+  const float* part = blockIdx.y == 0 ? part_a : part_b;
+  O* out = blockIdx.y == 0 ? out_a : out_b;
   const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
   if (c < cols)
@@ -196,16 +245,35 @@ using namespace adapcc;
 
 extern "C" {
 
-static int ln_grid(int rows) { return std::max(1, std::min((rows + kLnWarps - 1) / kLnWarps, 148 * 2)); }
-int adapcc_ln_partials(int rows) { return ln_grid(rows); }
+// Persistent grid: at most `per_sm` CTAs per SM (what the launch bounds make resident), shrunk so that
+// every CTA runs the same number of row-group iterations (8192 rows, 444 slots -> 342 CTAs x 3).
+static int ln_grid(int rows, int per_sm) {
+  const int groups = std::max(1, (rows + kLnWarps - 1) / kLnWarps);
+  const int cap = 148 * per_sm;
+  const int iters = (groups + cap - 1) / cap;
+  return (groups + iters - 1) / iters;
+}
+static int ln_fwd_ctas_per_sm(int d) { return d <= 768 ? 3 : 2; }   // = the kernels' __launch_bounds__
+static int ln_bwd_ctas_per_sm(int d) { return d <= 768 ? 2 : 1; }
+int adapcc_ln_partials(int rows) { return ln_grid(rows, 2); }       // upper bound of the backward grid
 
-int adapcc_ln_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int rows,
-                  int d, float eps, void* stream) {
+// y = LayerNorm(x [+ res]); when res != nullptr the bf16 sum x + res is also written to sum_out.
+static int ln_fwd_launch(const void* x, const void* res, const void* gamma, const void* beta, void* sum_out, void* y,
+                         float* mean, float* rstd, int rows, int d, float eps, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (rows <= 0) return 0;
-  const int grid = ln_grid(rows);
-#define LN_FWD(V) ln_fwd_kernel<V><<<grid, kLnWarps * 32, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, \
-    (const __nv_bfloat16*)beta, (__nv_bfloat16*)y, mean, rstd, rows, eps)
+  const int grid = ln_grid(rows, ln_fwd_ctas_per_sm(d));
+#define LN_FWD(V)                                                                                                  \
+  do {                                                                                                             \
+    if (res)                                                                                                       \
+      ln_fwd_kernel<V, true><<<grid, kLnWarps * 32, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res,    \
+          (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (__nv_bfloat16*)sum_out, (__nv_bfloat16*)y,     \
+          mean, rstd, rows, eps);                                                                                  \
+    else                                                                                                           \
+      ln_fwd_kernel<V, false><<<grid, kLnWarps * 32, 0, s>>>((const __nv_bfloat16*)x, nullptr,                     \
+          (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, nullptr, (__nv_bfloat16*)y, mean, rstd, rows,   \
+          eps);                                                                                                    \
+  } while (0)
   switch (d) {
     case 256: LN_FWD(1); break;
     case 512: LN_FWD(2); break;
@@ -219,16 +287,36 @@ int adapcc_ln_fwd(const void* x, const void* gamma, const void* beta, void* y, f
   return 0;
 }
 
+int adapcc_ln_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int rows,
+                  int d, float eps, void* stream) {
+  return ln_fwd_launch(x, nullptr, gamma, beta, nullptr, y, mean, rstd, rows, d, eps, stream);
+}
+
+int adapcc_add_ln_fwd(const void* x, const void* res, const void* gamma, const void* beta, void* sum_out, void* y,
+                      float* mean, float* rstd, int rows, int d, float eps, void* stream) {
+  if (!res || !sum_out) { set_error("add_ln_fwd: res and sum_out are required"); return -1; }
+  return ln_fwd_launch(x, res, gamma, beta, sum_out, y, mean, rstd, rows, d, eps, stream);
+}
+
 // part: fp32 scratch of 2 * adapcc_ln_partials(rows) * d floats. dgamma/dbeta: bf16 [d].
-int adapcc_ln_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dx,
-                  void* dgamma, void* dbeta, float* part, int rows, int d, void* stream) {
+// dres (optional, bf16 [rows, d]): gradient of the residual stream, added to dx in the same pass.
+static int ln_bwd_launch(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                         const void* dres, void* dx, void* dgamma, void* dbeta, float* part, int rows, int d,
+                         void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (rows <= 0) return 0;
-  const int grid = ln_grid(rows);
+  const int grid = ln_grid(rows, ln_bwd_ctas_per_sm(d));
   float* pg = part;
   float* pb = part + (size_t)grid * d;
-#define LN_BWD(V) ln_bwd_kernel<V><<<grid, kLnWarps * 32, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, \
-    (const __nv_bfloat16*)gamma, mean, rstd, (__nv_bfloat16*)dx, pg, pb, rows)
+#define LN_BWD(V)                                                                                                  \
+  do {                                                                                                             \
+    if (dres)                                                                                                      \
+      ln_bwd_kernel<V, true><<<grid, kLnWarps * 32, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,     \
+          (const __nv_bfloat16*)gamma, mean, rstd, (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, pg, pb, rows);  \
+    else                                                                                                           \
+      ln_bwd_kernel<V, false><<<grid, kLnWarps * 32, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,    \
+          (const __nv_bfloat16*)gamma, mean, rstd, nullptr, (__nv_bfloat16*)dx, pg, pb, rows);                     \
+  } while (0)
   switch (d) {
     case 256: LN_BWD(1); break;
     case 512: LN_BWD(2); break;
@@ -238,11 +326,22 @@ int adapcc_ln_bwd(const void* dy, const void* x, const void* gamma, const float*
   }
 #undef LN_BWD
   CUDA_TRY(cudaGetLastError());
-  colsum_finalize_kernel<__nv_bfloat16><<<(d + 31) / 32, dim3(32, 32), 0, s>>>(pg, grid, d, (__nv_bfloat16*)dgamma);
-  colsum_finalize_kernel<__nv_bfloat16><<<(d + 31) / 32, dim3(32, 32), 0, s>>>(pb, grid, d, (__nv_bfloat16*)dbeta);
+  colsum_finalize_pair_kernel<__nv_bfloat16><<<dim3((d + 31) / 32, 2), dim3(32, 32), 0, s>>>(
+      pg, pb, grid, d, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta);
   CUDA_TRY(cudaGetLastError());
-  count_launch(3);
+  count_launch(2);
   return 0;
+}
+
+int adapcc_ln_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dx,
+                  void* dgamma, void* dbeta, float* part, int rows, int d, void* stream) {
+  return ln_bwd_launch(dy, x, gamma, mean, rstd, nullptr, dx, dgamma, dbeta, part, rows, d, stream);
+}
+
+int adapcc_add_ln_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                      const void* dres, void* dx, void* dgamma, void* dbeta, float* part, int rows, int d,
+                      void* stream) {
+  return ln_bwd_launch(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, part, rows, d, stream);
 }
 
 int adapcc_colsum_splits(int rows) { return std::max(1, std::min(64, rows / 64)); }

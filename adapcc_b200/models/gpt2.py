@@ -10,8 +10,9 @@ architecture written for B200 training:
 * parameters live in bf16 (fp32 master copy inside the fused optimizer), so gradients are born in
   bf16 and the gradient all-reduce moves half the bytes with fp32 accumulation in the kernel;
 * attention goes through ``scaled_dot_product_attention`` (flash kernels), MLP through cuBLAS;
-* the LM head + cross-entropy is evaluated in row chunks so the [tokens, vocab] logits are never
-  materialised at once (50 262 x 8192 x 4 B = 1.6 GB otherwise);
+* the LM head + cross-entropy is one fused pass per row chunk: bf16 logits from the GEMM, a softmax-CE
+  kernel that overwrites them in place with their gradient, and the two backward GEMMs right away — fp32
+  logits / probabilities (50 304 x 8192 x 4 B = 1.6 GB each in the stock path) never exist;
 * no data-dependent host syncs: the whole step can be captured in one CUDA graph.
 
 Token-type embeddings reuse ``wte`` exactly as HF GPT-2 does.
@@ -19,6 +20,7 @@ Token-type embeddings reuse ``wte`` exactly as HF GPT-2 does.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -38,7 +40,8 @@ class GPT2Config:
     n_head: int = 12
     layer_norm_epsilon: float = 1e-5
     initializer_range: float = 0.02
-    lm_chunk_rows: int = 2048            # rows of the fused LM-head/CE evaluated at a time
+    lm_chunk_rows: int = 8192            # rows of the fused LM-head/CE evaluated at a time (bf16 logits of one
+                                         # chunk: 8192 x 50304 x 2 B = 0.8 GB; measured 2 % faster per step than 2048)
 
     @classmethod
     def tiny(cls) -> "GPT2Config":
@@ -58,17 +61,28 @@ class Block(nn.Module):
         self.c_fc = FusedLinear(d, 4 * d)
         self.c_proj2 = FusedLinear(4 * d, d)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        B, T, D = x.shape
-        h = self.ln_1(x)
+    def _attn(self, h: torch.Tensor) -> torch.Tensor:
+        B, T, D = h.shape
         # split along the feature dim (views; measured 6 % faster fwd+bwd than the packed permute:
         # the backward writes dq/dk/dv straight into one [B, T, 3D] buffer layout-wise)
         q, k, v = (t.view(B, T, self.n_head, D // self.n_head).transpose(1, 2) for t in self.c_attn(h).split(D, dim=-1))
         a = F.scaled_dot_product_attention(q, k, v, is_causal=True)
-        x = x + self.c_proj(a.transpose(1, 2).reshape(B, T, D))
-        h = self.ln_2(x)
-        x = x + self.c_proj2(F.gelu(self.c_fc(h), approximate="tanh"))
-        return x
+        return self.c_proj(a.transpose(1, 2).reshape(B, T, D))
+
+    def forward_deferred(self, x: torch.Tensor, delta: Optional[torch.Tensor]):
+        """Same block with every residual add fused into the LayerNorm that follows it: takes the
+        residual stream ``x`` and the previous block's not-yet-added MLP output ``delta``, returns
+        (stream, this block's not-yet-added MLP output)."""
+        if delta is None:
+            h = self.ln_1(x)
+        else:
+            x, h = self.ln_1.forward_add(x, delta)
+        x, h = self.ln_2.forward_add(x, self._attn(h))
+        return x, self.c_proj2(F.gelu(self.c_fc(h), approximate="tanh"))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = x + self._attn(self.ln_1(x))
+        return x + self.c_proj2(F.gelu(self.c_fc(self.ln_2(x)), approximate="tanh"))
 
 
 class _ChunkedLMLoss(torch.autograd.Function):
@@ -81,7 +95,7 @@ class _ChunkedLMLoss(torch.autograd.Function):
         n = h.shape[0]
         use_kernel = h.is_cuda and h.dtype == torch.bfloat16 and weight.shape[0] % 8 == 0
         grad_h = torch.empty_like(h)
-        grad_w = torch.zeros(weight.shape, dtype=torch.float32, device=h.device)
+        grad_w = None
         total = torch.zeros((), dtype=torch.float32, device=h.device)
         if use_kernel:
             from ..ops import fused_ce_
@@ -102,9 +116,16 @@ class _ChunkedLMLoss(torch.autograd.Function):
                 p = torch.softmax(lf, dim=-1)
                 p.scatter_add_(1, ls.clamp(min=0).unsqueeze(1), -torch.ones_like(p[:, :1]))
                 g = (p * valid.unsqueeze(1)).to(h.dtype)
-            grad_h[s:s + chunk] = g @ weight
-            grad_w += (g.t() @ hs).float()
-        ctx.save_for_backward(grad_h, grad_w.to(weight.dtype))
+            torch.mm(g, weight, out=grad_h[s:s + chunk])
+            # dW accumulates across chunks inside the GEMM (fp32 accumulator, beta = 1 epilogue) — an
+            # fp32 side buffer cost ~1 GB of extra HBM traffic per chunk at vocab 50304
+            if grad_w is None:
+                grad_w = g.t() @ hs
+            else:
+                grad_w.addmm_(g.t(), hs)
+        if grad_w is None:
+            grad_w = torch.zeros_like(weight)
+        ctx.save_for_backward(grad_h, grad_w)
         return total
 
     @staticmethod
@@ -125,6 +146,12 @@ class GPT2DoubleHeads(nn.Module):
         self.h = nn.ModuleList([Block(cfg) for _ in range(cfg.n_layer)])
         self.ln_f = FusedLayerNorm(cfg.n_embd, eps=cfg.layer_norm_epsilon)
         self.mc_head = nn.Linear(cfg.n_embd, 1)           # SequenceSummary(summary_type="cls_index")
+        # > 0: evaluate the LM head only on (at most) this many rows whose label is not -100. Rows with
+        # an ignored label contribute neither loss nor gradient, so the result is identical; PersonaChat
+        # batches score only the last candidate's reply, i.e. ~1/8 of the rows at the bench shape.
+        self.lm_row_capacity = 0
+        # residual adds fused into the following LayerNorm (fwd) / its input gradient (bwd)
+        self.fuse_add_ln = os.environ.get("ADAPCC_FUSE_ADD_LN", "0") == "1"
         self.apply(self._init)
         for blk in self.h:                                  # GPT-2 residual-projection scaling
             for lin in (blk.c_proj, blk.c_proj2):
@@ -145,6 +172,11 @@ class GPT2DoubleHeads(nn.Module):
         x = self.wte(input_ids) + self.wpe(pos)[None]
         if token_type_ids is not None:
             x = x + self.wte(token_type_ids)
+        if self.fuse_add_ln:
+            delta = None
+            for blk in self.h:
+                x, delta = blk.forward_deferred(x, delta)
+            return self.ln_f.forward_add(x, delta)[1]
         for blk in self.h:
             x = blk(x)
         return self.ln_f(x)
@@ -163,9 +195,20 @@ class GPT2DoubleHeads(nn.Module):
             labels = lm_labels.reshape(B * C, T)
             shift_h = h[:, :-1].reshape(-1, h.shape[-1])
             shift_l = labels[:, 1:].reshape(-1)
-            n_valid = (shift_l >= 0).sum().clamp(min=1)
+            n_valid = (shift_l >= 0).sum()
+            cap = int(self.lm_row_capacity)
+            compact = 0 < cap < shift_l.numel()
+            if compact:
+                # scored rows first, in their original order (stable sort; static shapes, so the step
+                # stays CUDA-graph capturable). Backward scatters the row gradients back.
+                order = torch.argsort((shift_l < 0).to(torch.int8), stable=True)[:cap]
+                shift_h = shift_h.index_select(0, order)
+                shift_l = shift_l.index_select(0, order)
             lm_loss = _ChunkedLMLoss.apply(shift_h, self.wte.weight, shift_l, self.cfg.lm_chunk_rows,
-                                           self.cfg.vocab_size) / n_valid
+                                           self.cfg.vocab_size) / n_valid.clamp(min=1)
+            if compact:
+                # a batch with more scored rows than the capacity must not train silently on a subset
+                lm_loss = torch.where(n_valid > cap, torch.full_like(lm_loss, float("nan")), lm_loss)
         if mc_token_ids is not None and mc_labels is not None:
             idx = mc_token_ids.reshape(B * C, 1, 1).expand(-1, 1, h.shape[-1])
             cls_h = h.gather(1, idx).squeeze(1)                               # [B*C, D]
@@ -173,6 +216,13 @@ class GPT2DoubleHeads(nn.Module):
             mc_loss = F.cross_entropy(mc_logits, mc_labels)
         loss = lm_coef * lm_loss + mc_coef * mc_loss
         return loss, lm_loss, mc_loss
+
+
+def lm_rows_needed(lm_labels: torch.Tensor, multiple: int = 256) -> int:
+    """Capacity for ``GPT2DoubleHeads.lm_row_capacity`` from a (host) label tensor [B, C, T]: the number
+    of scored next-token rows, rounded up to ``multiple``."""
+    n = int((lm_labels[..., 1:] >= 0).sum())
+    return max(multiple, (n + multiple - 1) // multiple * multiple)
 
 
 def synthetic_batch(batch: int, candidates: int, seq_len: int, vocab: int, device="cpu", seed: int = 0,

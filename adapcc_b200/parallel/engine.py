@@ -19,6 +19,7 @@ mean over the active ranks, clip + AdamW — but lays memory out for the hardwar
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence
 
@@ -34,14 +35,36 @@ class _Bucket:
     pending: int = 0
 
 
+class _GradSink:
+    """Handed to the fused ops (ops/layers.py::_sink) through ``param._adapcc_grad_sink``: the op writes
+    the parameter's gradient straight into its view of the flat buffer and reports it here."""
+    __slots__ = ("engine", "index", "written")
+
+    def __init__(self, engine: "FlatDataParallel", index: int):
+        self.engine, self.index, self.written = engine, index, False
+
+    def begin(self) -> bool:
+        if self.written:
+            raise RuntimeError("a parameter with direct gradient writes produced a second gradient in one step "
+                               "(module applied twice / tied weights): build the engine with direct_grads=False")
+        self.written = True
+        return True
+
+    def done(self) -> None:
+        self.engine._grad_ready(self.index)
+
+
 class FlatDataParallel:
     def __init__(self, model: nn.Module, comm=None, *, world_size: int = 1, rank: int = 0,
                  bucket_mb: float = 32.0, lr: float = 6.25e-5, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.01, max_norm: float = 1.0, optimizer: str = "adamw",
                  param_dtype: torch.dtype = torch.bfloat16, algo: str = "auto", active: Optional[Sequence[int]] = None,
-                 comm_fn: Optional[Callable] = None):
+                 comm_fn: Optional[Callable] = None, direct_grads: Optional[bool] = None):
         """``comm``: a :class:`~adapcc_b200.runtime.native.NativeComm` (or None for one GPU).
-        ``comm_fn(flat_slice)``: alternative collective (e.g. an NCCL all-reduce) for baselines."""
+        ``comm_fn(flat_slice)``: alternative collective (e.g. an NCCL all-reduce) for baselines.
+        ``direct_grads``: FusedLinear / FusedLayerNorm backward kernels write their parameter gradients
+        straight into the flat buffer (no per-parameter accumulate kernel). Requires every such module to
+        be applied once per step; default on (``ADAPCC_DIRECT_GRADS=0`` turns it off)."""
         self.model, self.comm, self.world_size, self.rank = model, comm, world_size, rank
         self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
         self.optimizer, self.algo, self.comm_fn = optimizer, algo, comm_fn
@@ -94,6 +117,25 @@ class FlatDataParallel:
                 self.buckets.append(_Bucket(start, end, len(members)))
                 end, members = start, []
         self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(params)]
+        if direct_grads is None:
+            direct_grads = os.environ.get("ADAPCC_DIRECT_GRADS", "1") != "0"
+        self._sinks: List[_GradSink] = []
+        if direct_grads and dev.type == "cuda":
+            from ..ops.layers import FusedLayerNorm, FusedLinear
+            index = {id(p): i for i, p in enumerate(params)}
+            uses: Dict[int, int] = {}
+            fused = [m for m in model.modules() if isinstance(m, (FusedLinear, FusedLayerNorm))]
+            for m in fused:
+                for p in (m.weight, m.bias):
+                    if p is not None:
+                        uses[id(p)] = uses.get(id(p), 0) + 1
+            for m in fused:
+                for p in (m.weight, m.bias):
+                    if p is not None and id(p) in index and uses[id(p)] == 1 and p.dtype == param_dtype:
+                        sink = _GradSink(self, index[id(p)])
+                        p._adapcc_grad_sink = sink
+                        self._sinks.append(sink)
+        self.direct_grads = bool(self._sinks)
         self.comm_stream = torch.cuda.Stream(device=dev, priority=-1) if dev.type == "cuda" else None
         self._graph = None
         self._static: Dict[str, torch.Tensor] = {}
@@ -102,12 +144,15 @@ class FlatDataParallel:
         self.native_launches_per_step = 0
 
     # -- gradient hooks ---------------------------------------------------------------------------
+    def _grad_ready(self, i: int) -> None:
+        b = self.buckets[self._bucket_of[i]]
+        b.pending -= 1
+        if b.pending == 0:
+            self._launch_bucket(b)
+
     def _make_hook(self, i: int):
         def hook(_p):
-            b = self.buckets[self._bucket_of[i]]
-            b.pending -= 1
-            if b.pending == 0:
-                self._launch_bucket(b)
+            self._grad_ready(i)
         return hook
 
     def _launch_bucket(self, b: _Bucket) -> None:
@@ -131,6 +176,8 @@ class FlatDataParallel:
         self._forked = False
         for b in self.buckets:
             b.pending = b.n_params
+        for sink in self._sinks:
+            sink.written = False
         out = self.model(**batch)
         loss = out[0] if isinstance(out, (tuple, list)) else out
         loss.backward()
@@ -190,4 +237,9 @@ class FlatDataParallel:
     def close(self) -> None:
         for h in self._hooks:
             h.remove()
+        for sink in self._sinks:
+            p = self.params[sink.index]
+            if getattr(p, "_adapcc_grad_sink", None) is sink:
+                del p._adapcc_grad_sink
+        self._sinks = []
         self._graph = None

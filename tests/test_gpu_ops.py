@@ -201,6 +201,113 @@ def test_fused_layernorm_matches_torch(dev, d):
         assert err < 2e-2, err
 
 
+@pytest.mark.parametrize("d", [256, 768])
+def test_fused_add_layernorm_matches_torch(dev, d):
+    """(x, res) -> (x + res, LN(x + res)) and its backward with a residual-stream gradient."""
+    from adapcc_b200.ops.layers import FusedLayerNorm
+
+    torch.manual_seed(d + 1)
+    rows = 2051
+    ln = FusedLayerNorm(d).to(dev).bfloat16()
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(d) * 0.5 + 1)
+        ln.bias.copy_(torch.randn(d) * 0.1)
+    x = (torch.randn(rows, d, device=dev) * 2).bfloat16().requires_grad_(True)
+    r = (torch.randn(rows, d, device=dev) + 0.5).bfloat16().requires_grad_(True)
+    dy = torch.randn(rows, d, device=dev).bfloat16()
+    ds = torch.randn(rows, d, device=dev).bfloat16()
+    s, y = ln.forward_add(x, r)
+    torch.autograd.backward([s, y], [ds, dy])
+    # the sum is exactly the bf16 add
+    assert torch.equal(s, x.detach() + r.detach())
+    xr = x.detach().float().requires_grad_(True)
+    rr = r.detach().float().requires_grad_(True)
+    wr = ln.weight.detach().float().requires_grad_(True)
+    br = ln.bias.detach().float().requires_grad_(True)
+    # the same bf16-rounded sum, with the gradient passing straight through the rounding
+    sr = (xr + rr) + ((xr + rr).bfloat16().float() - (xr + rr)).detach()
+    yr = torch.nn.functional.layer_norm(sr, (d,), wr, br, ln.eps)
+    torch.autograd.backward([sr, yr], [ds.float(), dy.float()])
+    assert torch.allclose(y.float(), yr, atol=3e-2, rtol=2e-2)
+    assert torch.allclose(x.grad.float(), xr.grad, atol=6e-2, rtol=5e-2)
+    assert torch.equal(x.grad, r.grad)
+    for got, want in ((ln.weight.grad, wr.grad), (ln.bias.grad, br.grad)):
+        err = (got.float() - want).abs().max() / want.abs().max()
+        assert err < 2e-2, err
+    # unused sum (the final LayerNorm of the network): gradient is the plain LayerNorm one
+    x2 = x.detach().clone().requires_grad_(True)
+    r2 = r.detach().clone().requires_grad_(True)
+    ln.zero_grad()
+    ln.forward_add(x2, r2)[1].backward(dy)
+    x3 = (x.detach() + r.detach()).requires_grad_(True)
+    ln(x3).backward(dy)
+    assert torch.equal(x2.grad, x3.grad)
+
+
+def test_gpt2_fused_residual_path_matches_unfused(dev):
+    """d = 256 so the fused LayerNorm kernels run; deferred-residual blocks vs plain blocks, and the
+    LM head on scored rows only vs all rows, eager and under CUDA-graph capture."""
+    from adapcc_b200.models.gpt2 import GPT2Config, GPT2DoubleHeads, lm_rows_needed, synthetic_batch
+    from adapcc_b200.parallel.engine import FlatDataParallel
+
+    cfg = GPT2Config(vocab_size=1000, n_positions=64, n_embd=256, n_layer=3, n_head=4, lm_chunk_rows=96)
+    torch.manual_seed(11)
+    base = GPT2DoubleHeads(cfg).to(dev).bfloat16()
+    batch = synthetic_batch(2, 2, 64, cfg.vocab_size, device=dev)
+    need = lm_rows_needed(batch["lm_labels"], multiple=16)
+
+    def run(fuse, cap):
+        m = GPT2DoubleHeads(cfg).to(dev).bfloat16()
+        m.load_state_dict(base.state_dict())
+        m.fuse_add_ln, m.lm_row_capacity = fuse, cap
+        loss = m(**batch)[0]
+        loss.backward()
+        return loss.item(), torch.cat([p.grad.float().flatten() for p in m.parameters()])
+
+    l0, g0 = run(False, 0)
+    for fuse, cap in ((True, 0), (False, need), (True, need)):
+        l1, g1 = run(fuse, cap)
+        assert abs(l1 - l0) < 2e-2 * abs(l0), (fuse, cap, l0, l1)
+        cos = torch.nn.functional.cosine_similarity(g0, g1, dim=0)
+        assert cos > 0.995, (fuse, cap, cos)
+    # whole step captured in a graph with both options on
+    torch.manual_seed(12)
+    m = GPT2DoubleHeads(cfg).to(dev)
+    m.fuse_add_ln, m.lm_row_capacity = True, need
+    eng = FlatDataParallel(m, None, world_size=1, lr=2e-3, max_norm=1.0)
+    eng.capture(batch, warmup=1)
+    out = [float(eng.step_graph(batch).item()) for _ in range(8)]
+    assert out[-1] < out[0] - 0.1, out
+    eng.close()
+
+
+def test_engine_direct_grads_match_accumulated(dev):
+    """Fused ops writing parameter gradients straight into the flat buffer vs autograd accumulation."""
+    from adapcc_b200.models.gpt2 import GPT2Config, GPT2DoubleHeads, synthetic_batch
+    from adapcc_b200.parallel.engine import FlatDataParallel
+
+    cfg = GPT2Config(vocab_size=1000, n_positions=64, n_embd=256, n_layer=2, n_head=4, lm_chunk_rows=96)
+    batch = synthetic_batch(2, 2, 64, cfg.vocab_size, device=dev)
+    grads, losses = {}, {}
+    for direct in (False, True):
+        torch.manual_seed(21)
+        m = GPT2DoubleHeads(cfg).to(dev)
+        m.fuse_add_ln = direct                              # cover both LayerNorm backward variants
+        eng = FlatDataParallel(m, None, world_size=1, lr=1e-3, max_norm=1.0, direct_grads=direct)
+        assert eng.direct_grads == direct
+        eng.step(batch)
+        grads[direct] = eng.flat_grad.float().clone()
+        losses[direct] = [float(eng.step(batch).item()) for _ in range(4)]
+        eng.close()
+        assert not any(hasattr(p, "_adapcc_grad_sink") for p in m.parameters())
+    ref = grads[False]
+    assert ref.abs().max() > 0
+    assert (grads[True] - ref).abs().max() <= 5e-2 * ref.abs().max()
+    cos = torch.nn.functional.cosine_similarity(grads[True], ref, dim=0)
+    assert cos > 0.995, cos
+    assert abs(losses[True][-1] - losses[False][-1]) < 0.03 * abs(losses[False][-1])
+
+
 def test_fused_linear_bias_grad(dev):
     from adapcc_b200.ops.layers import FusedLinear
 

@@ -1,0 +1,55 @@
+"""CPU checks of the workload models (fp32 reference paths; the fused CUDA paths are in test_gpu_ops.py)."""
+import torch
+
+from adapcc_b200.models.gpt2 import GPT2Config, GPT2DoubleHeads, lm_rows_needed, synthetic_batch
+
+
+def _grads(m):
+    return torch.cat([p.grad.flatten() for p in m.parameters()])
+
+
+def test_gpt2_double_heads_loss_matches_plain_cross_entropy():
+    torch.manual_seed(0)
+    cfg = GPT2Config.tiny()
+    m = GPT2DoubleHeads(cfg)
+    b = synthetic_batch(2, 2, 32, cfg.vocab_size)
+    loss, lm, mc = m(**b)
+    B, C, T = b["input_ids"].shape
+    h = m.hidden(b["input_ids"].reshape(B * C, T), b["token_type_ids"].reshape(B * C, T))
+    logits = (h @ m.wte.weight.t())[..., :cfg.vocab_size]
+    ref_lm = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, cfg.vocab_size),
+                                               b["lm_labels"].reshape(B * C, T)[:, 1:].reshape(-1), ignore_index=-100)
+    assert torch.allclose(lm, ref_lm, atol=1e-5)
+    assert torch.isfinite(mc) and torch.allclose(loss, lm + mc)
+
+
+def test_lm_head_on_scored_rows_only_is_equivalent():
+    torch.manual_seed(0)
+    cfg = GPT2Config.tiny()
+    m = GPT2DoubleHeads(cfg)
+    b = synthetic_batch(2, 2, 32, cfg.vocab_size)
+    need = lm_rows_needed(b["lm_labels"], multiple=8)
+    assert need == 16                                    # 2 dialogues x 8 reply tokens of the last candidate
+    loss0, _, _ = m(**b)
+    loss0.backward()
+    g0 = _grads(m).clone()
+    for cap in (need, need + 8):                         # exact fit and with padding rows
+        m.zero_grad()
+        m.lm_row_capacity = cap
+        loss1, _, _ = m(**b)
+        loss1.backward()
+        assert torch.allclose(loss0, loss1, atol=1e-6)
+        assert torch.allclose(g0, _grads(m), atol=1e-6)
+    m.lm_row_capacity = need - 8                         # too small: loud, not a silent subset
+    assert torch.isnan(m(**b)[0])
+
+
+def test_vit_steps_on_cpu():
+    from adapcc_b200.models.vit import ViT, ViTConfig
+    torch.manual_seed(0)
+    vit = ViT(ViTConfig.tiny())
+    x = torch.randn(2, 3, vit.cfg.image_size, vit.cfg.image_size)
+    out = vit(x)
+    assert out.shape == (2, vit.cfg.num_classes)
+    out.sum().backward()
+    assert all(p.grad is not None for p in vit.parameters())
