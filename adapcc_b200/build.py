@@ -40,6 +40,21 @@ def sources() -> list[Path]:
     return sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")))
 
 
+def tool_sources() -> list[Path]:
+    """Stand-alone binaries (csrc/bin/*.cu -> _C/<name>), e.g. ``check_p2p``."""
+    return sorted((CSRC / "bin").glob("*.cu"))
+
+
+def _build_tool(src: Path) -> str:
+    out = OUT_DIR / src.stem
+    cmd = [_nvcc(), *GENCODE, "-O3", "-std=c++17", "-lineinfo", "-I", str(CSRC), str(src), "-o", str(out),
+           "-cudart", "static", "-ldl", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"tool build failed: {src.name}\n$ {' '.join(cmd)}\n{r.stdout}{r.stderr}")
+    return f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}"
+
+
 def _digest(paths: list[Path]) -> str:
     h = hashlib.sha256()
     for p in sorted(paths):
@@ -71,14 +86,18 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     srcs = sources()
     hdrs = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh"))
     stamp = OUT_DIR / "build.stamp"
-    want = _digest(srcs + hdrs)
-    if not force and LIB.exists() and stamp.exists() and stamp.read_text().strip() == want:
+    tools = tool_sources()
+    want = _digest(srcs + hdrs + tools)
+    have_tools = all((OUT_DIR / t.stem).exists() for t in tools)
+    if not force and LIB.exists() and have_tools and stamp.exists() and stamp.read_text().strip() == want:
         return LIB
     BUILD_DIR.mkdir(parents=True, exist_ok=True)
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        tool_logs = [ex.submit(_build_tool, t) for t in tools]
         results = list(ex.map(lambda s: _compile(s, verbose), srcs))
+        tool_logs = [f.result() for f in tool_logs]
     objs = [str(o) for o, _ in results]
-    (OUT_DIR / "build.log").write_text("\n".join(log for _, log in results))
+    (OUT_DIR / "build.log").write_text("\n".join([log for _, log in results] + tool_logs))
     cmd = [_nvcc(), "-shared", *GENCODE, "-o", str(LIB), *objs, "-cudart", "static", "-ldl", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -21,7 +21,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from adapcc_b200 import ALLREDUCE  # noqa: E402
 from adapcc_b200.adapcc import AdapCC  # noqa: E402
-from adapcc_b200.models.gpt2 import GPT2Config, GPT2DoubleHeads, synthetic_batch  # noqa: E402
+from adapcc_b200.models.gpt2 import GPT2Config, GPT2DoubleHeads, lm_rows_needed, synthetic_batch  # noqa: E402
 from adapcc_b200.parallel.ddp import rebuild_buckets, wrap_ddp  # noqa: E402
 from adapcc_b200.parallel.engine import FlatDataParallel  # noqa: E402
 
@@ -45,6 +45,9 @@ def main():
     p.add_argument("--mc_coef", type=float, default=1.0)
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--tiny", action="store_true")
+    p.add_argument("--fuse_add_ln", action="store_true", help="residual adds fused into the following LayerNorm")
+    p.add_argument("--lm_rows", default="all", choices=["all", "scored"],
+                   help="scored: LM head only on rows with a label (same loss/gradients, ~1/8 of the rows)")
     a = p.parse_args()
 
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
@@ -64,6 +67,9 @@ def main():
     seq = min(a.seq_len, cfg.n_positions)
     batches = [synthetic_batch(a.train_batch_size, a.num_candidates, seq, cfg.vocab_size, device=dev, seed=rank * 100 + i)
                for i in range(4)]
+    model.fuse_add_ln = a.fuse_add_ln or model.fuse_add_ln
+    if a.lm_rows == "scored":                      # capacity from the host side of the loader, never a device sync
+        model.lm_row_capacity = max(lm_rows_needed(b["lm_labels"].cpu()) for b in batches)
     if a.engine == "flat":
         eng = FlatDataParallel(model, comm.native if world > 1 else None, world_size=world, rank=rank, lr=a.lr,
                                max_norm=a.max_norm)

@@ -5,3 +5,4 @@ EXTRA="" run nodirect ADAPCC_DIRECT_GRADS=0
 EXTRA="" run fuse ADAPCC_FUSE_ADD_LN=1
 EXTRA="--lm_rows scored" run fuse_scored ADAPCC_FUSE_ADD_LN=1
 ADAPCC_FUSE_ADD_LN=1 timeout 120 python tools/torch_profile_step.py --out gpurun_out/torch_profile_v3.md > gpurun_out/torch_profile_v3.log 2>&1; head -34 gpurun_out/torch_profile_v3.md
+timeout 60 adapcc_b200/_C/check_p2p --mb 256 --iters 3 > gpurun_out/check_p2p_1gpu.log 2>&1; tail -8 gpurun_out/check_p2p_1gpu.log
