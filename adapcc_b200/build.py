@@ -47,11 +47,13 @@ def tool_sources() -> list[Path]:
 
 def _build_tool(src: Path) -> str:
     out = OUT_DIR / src.stem
-    cmd = [_nvcc(), *GENCODE, "-O3", "-std=c++17", "-lineinfo", "-I", str(CSRC), str(src), "-o", str(out),
+    tmp = OUT_DIR / (src.stem + ".tmp")
+    cmd = [_nvcc(), *GENCODE, "-O3", "-std=c++17", "-lineinfo", "-I", str(CSRC), str(src), "-o", str(tmp),
            "-cudart", "static", "-ldl", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"tool build failed: {src.name}\n$ {' '.join(cmd)}\n{r.stdout}{r.stderr}")
+    os.replace(tmp, out)
     return f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}"
 
 
@@ -98,10 +100,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         tool_logs = [f.result() for f in tool_logs]
     objs = [str(o) for o, _ in results]
     (OUT_DIR / "build.log").write_text("\n".join([log for _, log in results] + tool_logs))
-    cmd = [_nvcc(), "-shared", *GENCODE, "-o", str(LIB), *objs, "-cudart", "static", "-ldl", "-lpthread"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    tmp = LIB.with_suffix(".so.tmp")                 # link aside, then rename: a reader (or a snapshot of the
+    cmd = [_nvcc(), "-shared", *GENCODE, "-o", str(tmp), *objs, "-cudart", "static", "-ldl", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)   # tree) never sees a half-written library
     if r.returncode != 0:
         raise RuntimeError(f"link failed\n$ {' '.join(cmd)}\n{r.stdout}{r.stderr}")
+    os.replace(tmp, LIB)
     stamp.write_text(want)
     return LIB
 

@@ -11,6 +11,10 @@
 #include <string>
 #include <vector>
 
+#include <fcntl.h>
+#include <unistd.h>
+
+#include "bootstrap.h"
 #include "comm_context.h"
 #include "driver_api.h"
 
@@ -172,6 +176,66 @@ void* adapcc_pool_alloc(ssize_t size, int device, void* stream) {
 }
 void adapcc_pool_free(void* ptr, ssize_t size, int device, void* stream) {
   (void)ptr; (void)size; (void)device; (void)stream;   // bump allocator: reclaimed with the context
+}
+
+// ---- bootstrap self-test (no GPU needed): every rank of a `world`-process group calls this with the
+// same name. Exercises the full mesh: allgather, fd exchange + fd broadcast over SCM_RIGHTS (each fd
+// is a pipe whose content names its owner, read back through the RECEIVED descriptor), barrier.
+// Returns 0, or a negative step number on failure (details in adapcc_last_error()).
+int adapcc_bootstrap_selftest(const char* name, int rank, int world, int timeout_ms) {
+  Bootstrap bs;
+  if (bs.init(name, rank, world, timeout_ms)) return -1;
+  std::vector<long long> all(world, -1);
+  const long long mine = 1000 + 7LL * rank;
+  if (bs.allgather(&mine, sizeof(mine), all.data())) return -2;
+  for (int r = 0; r < world; ++r)
+    if (all[r] != 1000 + 7LL * r) { set_error("allgather: slot %d holds %lld", r, all[r]); return -2; }
+  auto make_pipe = [](int tag, int* rd) -> int {      // a readable fd whose content is `tag`
+    int p[2];
+    if (pipe(p)) return -1;
+    const int n = (int)write(p[1], &tag, sizeof(tag));
+    close(p[1]);
+    *rd = p[0];
+    return n == (int)sizeof(tag) ? 0 : -1;
+  };
+  auto read_tag = [](int fd) -> int {
+    int tag = -1;
+    if (read(fd, &tag, sizeof(tag)) != (ssize_t)sizeof(tag)) return -1;
+    return tag;
+  };
+  // fd broadcast from the last rank
+  const int root = world - 1;
+  int my_fd = -1, got = -1;
+  if (rank == root && make_pipe(4242, &my_fd)) { set_error("pipe failed"); return -3; }
+  if (bs.bcast_fd(root, my_fd, &got)) return -3;
+  if (bs.barrier()) return -3;
+  // one pipe, world readers: only check that the descriptor is valid on every rank; the root reads it
+  if (got < 0 || fcntl(got, F_GETFD) < 0) { set_error("bcast_fd: invalid descriptor"); return -3; }
+  if (rank == root && read_tag(got) != 4242) { set_error("bcast_fd: wrong content"); return -3; }
+  if (got != my_fd) close(got);
+  if (my_fd >= 0) close(my_fd);
+  // all-to-all fd exchange: rank r's pipe holds (r + 1) tags of value 500 + r, one per reader
+  int p[2];
+  if (pipe(p)) { set_error("pipe failed"); return -4; }
+  for (int i = 0; i < world; ++i) {
+    const int tag = 500 + rank;
+    if (write(p[1], &tag, sizeof(tag)) != (ssize_t)sizeof(tag)) { set_error("pipe write failed"); return -4; }
+  }
+  close(p[1]);
+  std::vector<int> fds;
+  if (bs.exchange_fds(p[0], fds)) return -4;
+  if ((int)fds.size() != world) { set_error("exchange_fds: %d descriptors", (int)fds.size()); return -4; }
+  int rc = 0;
+  for (int r = 0; r < world; ++r) {
+    const int tag = read_tag(fds[r]);                 // every rank consumes exactly one tag per pipe
+    if (tag != 500 + r) { set_error("exchange_fds: fd of rank %d carried %d", r, tag); rc = -4; }
+  }
+  if (bs.barrier()) return -5;
+  for (int r = 0; r < world; ++r)
+    if (fds[r] >= 0 && fds[r] != p[0]) close(fds[r]);
+  close(p[0]);
+  bs.close_all();
+  return rc;
 }
 
 // ---- strategy / relay-control queries (no GPU needed; used by tests and the control plane)
