@@ -60,6 +60,15 @@ class Block(nn.Module):
         self.ln_2 = FusedLayerNorm(d, eps=cfg.layer_norm_epsilon)
         self.c_fc = FusedLinear(d, 4 * d)
         self.c_proj2 = FusedLinear(4 * d, d)
+        # experimental: c_fc + bias + GELU as ONE tcgen05 GEMM (ops/gemm.py); off unless asked for
+        self.tc_mlp = os.environ.get("ADAPCC_TCGEN05_MLP", "0") == "1"
+
+    def _mlp(self, h: torch.Tensor) -> torch.Tensor:
+        if self.tc_mlp and h.is_cuda and h.dtype == torch.bfloat16 and torch.is_grad_enabled():
+            from ..ops.gemm import linear_gelu, supported
+            if supported(h, self.c_fc.weight):
+                return self.c_proj2(linear_gelu(h, self.c_fc.weight, self.c_fc.bias))
+        return self.c_proj2(F.gelu(self.c_fc(h), approximate="tanh"))
 
     def _attn(self, h: torch.Tensor) -> torch.Tensor:
         B, T, D = h.shape
@@ -78,11 +87,11 @@ class Block(nn.Module):
         else:
             x, h = self.ln_1.forward_add(x, delta)
         x, h = self.ln_2.forward_add(x, self._attn(h))
-        return x, self.c_proj2(F.gelu(self.c_fc(h), approximate="tanh"))
+        return x, self._mlp(h)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = x + self._attn(self.ln_1(x))
-        return x + self.c_proj2(F.gelu(self.c_fc(self.ln_2(x)), approximate="tanh"))
+        return x + self._mlp(self.ln_2(x))
 
 
 class _ChunkedLMLoss(torch.autograd.Function):

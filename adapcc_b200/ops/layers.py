@@ -176,31 +176,37 @@ class _LinearFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        lib = _lib()
         x, w = ctx.saved_tensors
-        n = w.shape[0]
-        dy2 = dy.reshape(-1, n)
-        if not dy2.is_contiguous():
-            dy2 = dy2.contiguous()
-        x2 = x.reshape(-1, x.shape[-1])
-        dx = (dy2 @ w).view(x.shape) if ctx.needs_input_grad[0] else None
-        pw, pb = ctx.params
-        sw, sb = _sink(pw), _sink(pb)
-        if sw is not None and sw.begin():                 # GEMM straight into the flat gradient buffer
-            torch.mm(dy2.t(), x2, out=pw.grad)
-            sw.done()
-            dw = None
-        else:
-            sw, dw = None, dy2.t() @ x2
-        rows = dy2.shape[0]
-        direct_b = sb is not None and pb.grad.dtype == dy2.dtype and sb.begin()
-        db = pb.grad if direct_b else torch.empty(n, dtype=dy2.dtype, device=dy2.device)
-        part = torch.empty(lib.adapcc_colsum_splits(rows) * n, dtype=torch.float32, device=dy2.device)
-        if lib.adapcc_colsum(_p(dy2), rows, n, _p(db), _p(part), _s()) != 0:
-            raise NativeError(f"colsum failed: {last_error()}")
-        if direct_b:
-            sb.done()
-        return dx, dw, None if direct_b else db
+        return linear_backward(ctx.params, x, w, dy, ctx.needs_input_grad[0])
+
+
+def linear_backward(params, x, w, dy, needs_dx=True):
+    """(dx, dw, db) of y = x @ w.T + b for bf16 CUDA tensors: two GEMMs + the column-sum kernel; dw / db
+    go straight into the parameters' flat-buffer gradient views when the engine's sinks are attached."""
+    lib = _lib()
+    n = w.shape[0]
+    dy2 = dy.reshape(-1, n)
+    if not dy2.is_contiguous():
+        dy2 = dy2.contiguous()
+    x2 = x.reshape(-1, x.shape[-1])
+    dx = (dy2 @ w).view(x.shape) if needs_dx else None
+    pw, pb = params
+    sw, sb = _sink(pw), _sink(pb)
+    if sw is not None and sw.begin():                 # GEMM straight into the flat gradient buffer
+        torch.mm(dy2.t(), x2, out=pw.grad)
+        sw.done()
+        dw = None
+    else:
+        dw = dy2.t() @ x2
+    rows = dy2.shape[0]
+    direct_b = sb is not None and pb.grad.dtype == dy2.dtype and sb.begin()
+    db = pb.grad if direct_b else torch.empty(n, dtype=dy2.dtype, device=dy2.device)
+    part = torch.empty(lib.adapcc_colsum_splits(rows) * n, dtype=torch.float32, device=dy2.device)
+    if lib.adapcc_colsum(_p(dy2), rows, n, _p(db), _p(part), _s()) != 0:
+        raise NativeError(f"colsum failed: {last_error()}")
+    if direct_b:
+        sb.done()
+    return dx, dw, None if direct_b else db
 
 
 class FusedLinear(nn.Linear):

@@ -1,0 +1,52 @@
+"""EXPERIMENTAL tcgen05 GEMM (csrc/gemm_tcgen05.cu) against a plain PyTorch fp32 reference.
+
+Gated behind ADAPCC_EXPERIMENTAL=1 until the kernel has been through a GPU debugging session: a wrong
+descriptor bit ends in a trapped kernel, which would poison the CUDA context of the whole pytest process."""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("ADAPCC_EXPERIMENTAL", "0") != "1",
+                                 reason="experimental kernel: set ADAPCC_EXPERIMENTAL=1")]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("m,n,k,act", [(128, 256, 64, "none"), (256, 256, 128, "gelu"), (200, 384, 192, "gelu"),
+                                       (1024, 3072, 768, "gelu"), (384, 128, 3072, "none")])
+def test_gemm_bias_act_matches_fp32_reference(dev, m, n, k, act):
+    from adapcc_b200.ops.gemm import linear_act
+
+    torch.manual_seed(m + n + k)
+    x = torch.randn(m, k, device=dev).bfloat16()
+    w = (torch.randn(n, k, device=dev) / k ** 0.5).bfloat16()
+    b = torch.randn(n, device=dev).bfloat16()
+    out, pre = linear_act(x, w, b, act, save_pre=True)
+    torch.cuda.synchronize()
+    u = x.float() @ w.float().t() + b.float()
+    assert torch.allclose(pre.float(), u, atol=3e-2, rtol=2e-2), (pre.float() - u).abs().max()
+    want = torch.nn.functional.gelu(u.bfloat16().float(), approximate="tanh") if act == "gelu" else u
+    assert torch.allclose(out.float(), want, atol=3e-2, rtol=2e-2), (out.float() - want).abs().max()
+
+
+def test_linear_gelu_autograd_matches_torch(dev):
+    from adapcc_b200.ops.gemm import linear_gelu
+
+    torch.manual_seed(3)
+    x = torch.randn(4, 96, 256, device=dev).bfloat16().requires_grad_(True)
+    w = (torch.randn(1024, 256, device=dev) / 16).bfloat16().requires_grad_(True)
+    b = torch.randn(1024, device=dev).bfloat16().requires_grad_(True)
+    dy = torch.randn(4, 96, 1024, device=dev).bfloat16()
+    linear_gelu(x, w, b).backward(dy)
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    torch.nn.functional.gelu(torch.nn.functional.linear(xr, wr, br), approximate="tanh").backward(dy.float())
+    for got, want in ((x.grad, xr.grad), (w.grad, wr.grad), (b.grad, br.grad)):
+        err = (got.float() - want).abs().max() / want.abs().max()
+        assert err < 3e-2, err
