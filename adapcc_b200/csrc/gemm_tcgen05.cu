@@ -1,4 +1,6 @@
-// EXPERIMENTAL — compiled and SASS-checked (UTCHMMA / UTCBAR / UTMALDG / LDTM), NOT yet timed or tuned.
+// tcgen05 / TMEM / TMA GEMM with a fused epilogue. Numerically validated on B200 (tests/test_gpu_tcgen05.py: five
+// shapes incl. ragged M, both tile widths, K up to 3072, autograd); SASS: UTCHMMA, UTCBAR, UTMALDG.2D, LDTM.x32.
+// NOT yet timed or tuned against cuBLAS (one tile per CTA, no persistence, no CTA pairs) — hence opt-in.
 //
 // out[M, N] = act(A[M, K] · W[N, K]^T + bias[N])          (bf16 in, fp32 accumulate, bf16 out)
 // optionally also pre[M, N] = A · W^T + bias               (what the activation's backward needs)

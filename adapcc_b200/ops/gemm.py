@@ -1,4 +1,4 @@
-"""EXPERIMENTAL tcgen05 GEMM with a fused bias + GELU epilogue (csrc/gemm_tcgen05.cu).
+"""tcgen05 GEMM with a fused bias + GELU epilogue (csrc/gemm_tcgen05.cu); numerically validated on B200, untuned.
 
 ``linear_act(x, weight, bias, act)`` computes ``act(x @ weight.T + bias)`` for bf16 CUDA tensors with the
 accumulator in TMEM and the activation applied in the epilogue; ``linear_gelu`` is its autograd form (the

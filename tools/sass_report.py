@@ -10,7 +10,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "adapcc_b200", "_C", "libadapcc.so")
 KEYS = ["LDG.E.NA.128", "STG.E.128", "LDGMC", "STG.E.128.STRONG.SYS", "LDG.E.STRONG.SYS", "STG.E.STRONG.SYS",
-        "LDG.E.64.STRONG.SYS", "STG.E.64.STRONG.SYS", "MEMBAR.ALL.SYS", "CCTL.IVALL", "BAR.SYNC", "ATOMG", "REDG"]
+        "LDG.E.64.STRONG.SYS", "STG.E.64.STRONG.SYS", "MEMBAR.ALL.SYS", "CCTL.IVALL", "BAR.SYNC", "ATOMG", "REDG",
+        "UTCHMMA", "UTCBAR", "UTMALDG", "LDTM", "UTCATOMSWS", "SYNCS"]
 
 
 def main():
@@ -34,7 +35,8 @@ def main():
            "`multimem.ld_reduce` (in-switch NVLS reduction), `STG.E.128.STRONG.SYS` on a multicast address is "
            "`multimem.st`; `LDG.E.NA.128` / `STG.E.128` on mapped peer pointers are the 128-bit NVLink loads/stores; "
            "`MEMBAR.ALL.SYS` + `ST*.STRONG.SYS` / `LD*.STRONG.SYS` + `CCTL.IVALL` are the st.release.sys / "
-           "ld.acquire.sys flag protocol.", "",
+           "ld.acquire.sys flag protocol. `UTCHMMA` = tcgen05.mma (kind::f16), `UTCBAR` = tcgen05.commit, `UTMALDG` = TMA tensor "
+           "load, `LDTM` = tcgen05.ld (TMEM -> registers), `UTCATOMSWS` = tcgen05.alloc, `SYNCS` = mbarrier ops.", "",
            "| kernel family | instantiations | SASS instr | " + " | ".join(KEYS) + " |",
            "|---|---|---|" + "---|" * len(KEYS)]
     for k, d in fam.items():
