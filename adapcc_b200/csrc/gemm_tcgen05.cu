@@ -303,6 +303,195 @@ gemm_bias_act_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
   if (warp == 1) tmem_free<BN>(tmem_base);
 }
 
+// =====================================================================================================
+// Variant 1 (persistent; NOT yet run on a GPU — compiled and SASS-checked only, selected explicitly):
+//   grid = min(tiles, SMs); every CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...
+//   TMEM holds TWO accumulators (2 x BN columns): the MMA lane fills accumulator (i & 1) of its i-th tile
+//   while the epilogue warps drain the other one -> bias/GELU/stores overlap the next tile's MMAs, and the
+//   smem ring keeps streaming across tile boundaries (the producer never waits for an epilogue).
+//   Extra barriers: acc_full[2] (MMA -> epilogue, tcgen05.commit) and acc_empty[2] (epilogue -> MMA, one
+//   arrive per epilogue warp).
+// =====================================================================================================
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// bias + activation + bf16 stores of one 32-column chunk of one accumulator row (held by one thread)
+template <int ACT>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const __nv_bfloat16* __restrict__ bias32,
+                                               __nv_bfloat16* __restrict__ out32, __nv_bfloat16* __restrict__ pre32,
+                                               bool row_valid) {
+  float bf[32];
+  if (bias32 != nullptr) {
+    const uint4* bp = reinterpret_cast<const uint4*>(bias32);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const uint4 t = __ldg(bp + v);
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+        bf[v * 8 + 2 * j] = f.x;
+        bf[v * 8 + 2 * j + 1] = f.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bf[i] = 0.f;
+  }
+  uint32_t packed_out[16], packed_pre[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float u0 = __uint_as_float(acc[2 * i]) + bf[2 * i];
+    const float u1 = __uint_as_float(acc[2 * i + 1]) + bf[2 * i + 1];
+    __nv_bfloat162 pu = __floats2bfloat162_rn(u0, u1);
+    packed_pre[i] = *reinterpret_cast<uint32_t*>(&pu);
+    if (ACT == 1) {
+      const float2 r = __bfloat1622float2(pu);
+      __nv_bfloat162 po = __floats2bfloat162_rn(gelu_tanh(r.x), gelu_tanh(r.y));
+      packed_out[i] = *reinterpret_cast<uint32_t*>(&po);
+    } else {
+      packed_out[i] = packed_pre[i];
+    }
+  }
+  if (row_valid) {
+    uint4* o = reinterpret_cast<uint4*>(out32);
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      o[v] = make_uint4(packed_out[4 * v], packed_out[4 * v + 1], packed_out[4 * v + 2], packed_out[4 * v + 3]);
+    if (pre32 != nullptr) {
+      uint4* p = reinterpret_cast<uint4*>(pre32);
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        p[v] = make_uint4(packed_pre[4 * v], packed_pre[4 * v + 1], packed_pre[4 * v + 2], packed_pre[4 * v + 3]);
+    }
+  }
+}
+
+template <int BN>
+struct SmemP {
+  static constexpr uint32_t kABytes = kBM * kBK * 2;
+  static constexpr uint32_t kBBytes = BN * kBK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kBarOffset = kStages * kStageBytes;   // full[S], empty[S], acc_full[2], acc_empty[2], tmem ptr
+  static constexpr uint32_t kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
+  static constexpr uint32_t kDynamic = kTotal + 1024;
+};
+
+template <int BN, int ACT>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bias_act_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_a,
+                                        const __grid_constant__ CUtensorMap map_w,
+                                        const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                        __nv_bfloat16* __restrict__ pre, int M, int N, int K, int tiles_n,
+                                        int num_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  using S = SmemP<BN>;
+  constexpr int kTmemCols = 2 * BN;                              // 256 or 512: a power of two
+  const uint32_t bar0 = base + S::kBarOffset;
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (kStages + s); };
+  auto acc_full = [&](int a) { return bar0 + 8u * (2 * kStages + a); };
+  auto acc_empty = [&](int a) { return bar0 + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * kStages + 4);
+  auto smem_a = [&](int s) { return base + (uint32_t)s * S::kStageBytes; };
+  auto smem_b = [&](int s) { return base + (uint32_t)s * S::kStageBytes + S::kABytes; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = K / kBK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full(a), 1);
+      mbar_init(acc_empty(a), 4);                                // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: one continuous K-slab stream over all of this CTA's tiles =====
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = (int)(it % kStages);
+          const uint32_t ph = (it / kStages) & 1u;
+          mbar_wait(empty(s), ph ^ 1u);
+          mbar_expect_tx(full(s), S::kStageBytes);
+          tma_load_2d(smem_a(s), &map_a, kb * kBK, m_blk * kBM, full(s));
+          tma_load_2d(smem_b(s), &map_w, kb * kBK, n_blk * BN, full(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = instr_desc_bf16(kBM, BN);
+      uint32_t it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const uint32_t as = local & 1u, aph = (local >> 1) & 1u;
+        mbar_wait(acc_empty(as), aph ^ 1u);                      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * (uint32_t)BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = (int)(it % kStages);
+          const uint32_t ph = (it / kStages) & 1u;
+          mbar_wait(full(s), ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t da = smem_desc_k_sw128(smem_a(s) + (uint32_t)k * kUmmaK * 2);
+            const uint64_t db = smem_desc_k_sw128(smem_b(s) + (uint32_t)k * kUmmaK * 2);
+            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty(s));
+        }
+        umma_commit(acc_full(as));
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5 =====
+    const int q = warp & 3;
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+      const uint32_t as = local & 1u, aph = (local >> 1) & 1u;
+      mbar_wait(acc_full(as), aph);
+      tc_fence_after();
+      const int row = m_blk * kBM + q * 32 + lane;
+      const size_t row_off = (size_t)row * (size_t)N + (size_t)n_blk * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)BN + (uint32_t)(c * 32), acc);
+        epilogue_chunk<ACT>(acc, bias ? bias + (size_t)n_blk * BN + c * 32 : nullptr, out + row_off + c * 32,
+                            pre ? pre + row_off + c * 32 : nullptr, row < M);
+      }
+      // all of this warp's TMEM reads of accumulator `as` are complete (wait::ld inside tmem_ld_32x32)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(as));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_free<kTmemCols>(tmem_base);
+}
+
 // ---- host ----------------------------------------------------------------------------------------
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -355,6 +544,29 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const void* bias
   return 0;
 }
 
+template <int BN, int ACT>
+static int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mw, const void* bias, void* out, void* pre,
+                             int M, int N, int K, cudaStream_t s) {
+  auto kern = gemm_bias_act_tcgen05_persistent_kernel<BN, ACT>;
+  static bool configured = false;
+  static int sms = 0;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemP<BN>::kDynamic));
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    configured = true;
+  }
+  const int tiles_n = N / BN, tiles_m = (M + kBM - 1) / kBM;
+  const int num_tiles = tiles_n * tiles_m;
+  const int grid = num_tiles < sms ? num_tiles : sms;
+  kern<<<grid, kThreads, SmemP<BN>::kDynamic, s>>>(ma, mw, (const __nv_bfloat16*)bias, (__nv_bfloat16*)out,
+                                                   (__nv_bfloat16*)pre, M, N, K, tiles_n, num_tiles);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 }  // namespace tc
 }  // namespace adapcc
 
@@ -364,19 +576,31 @@ extern "C" {
 
 // out = act(a[M,K] @ w[N,K]^T + bias); pre (optional) = the pre-activation. bf16 row-major, 16-byte aligned.
 // Constraints of this first version: K % 64 == 0, N % 128 == 0 (256-wide tiles when N % 256 == 0).
-int adapcc_gemm_bias_act(const void* a, const void* w, const void* bias, void* out, void* pre, int M, int N, int K,
-                         int act, void* stream) {
+// variant 0: one tile per CTA (validated on B200). variant 1: persistent CTAs, double-buffered TMEM accumulator
+// (compiled only so far).
+int adapcc_gemm_bias_act_v(const void* a, const void* w, const void* bias, void* out, void* pre, int M, int N, int K,
+                           int act, int variant, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (K % tc::kBK != 0 || N % 128 != 0) { set_error("gemm_tcgen05: need K %% 64 == 0 and N %% 128 == 0 (got K=%d N=%d)", K, N); return -1; }
   if (act != 0 && act != 1) { set_error("gemm_tcgen05: act must be 0 (none) or 1 (gelu_tanh)"); return -1; }
+  if (variant != 0 && variant != 1) { set_error("gemm_tcgen05: variant must be 0 or 1"); return -1; }
   if (((uintptr_t)a | (uintptr_t)w | (uintptr_t)out | (uintptr_t)pre | (uintptr_t)bias) & 15) { set_error("gemm_tcgen05: operands must be 16-byte aligned"); return -1; }
   const int bn = (N % 256 == 0) ? 256 : 128;
   CUtensorMap ma, mw;
   if (tc::make_map(&ma, a, M, K, tc::kBM)) return -1;
   if (tc::make_map(&mw, w, N, K, bn)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
+  if (variant == 1) {
+    if (bn == 256) return act ? tc::launch_persistent<256, 1>(ma, mw, bias, out, pre, M, N, K, s) : tc::launch_persistent<256, 0>(ma, mw, bias, out, pre, M, N, K, s);
+    return act ? tc::launch_persistent<128, 1>(ma, mw, bias, out, pre, M, N, K, s) : tc::launch_persistent<128, 0>(ma, mw, bias, out, pre, M, N, K, s);
+  }
   if (bn == 256) return act ? tc::launch<256, 1>(ma, mw, bias, out, pre, M, N, K, s) : tc::launch<256, 0>(ma, mw, bias, out, pre, M, N, K, s);
   return act ? tc::launch<128, 1>(ma, mw, bias, out, pre, M, N, K, s) : tc::launch<128, 0>(ma, mw, bias, out, pre, M, N, K, s);
+}
+
+int adapcc_gemm_bias_act(const void* a, const void* w, const void* bias, void* out, void* pre, int M, int N, int K,
+                         int act, void* stream) {
+  return adapcc_gemm_bias_act_v(a, w, bias, out, pre, M, N, K, act, 0, stream);
 }
 
 }  // extern "C"

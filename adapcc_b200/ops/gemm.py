@@ -8,6 +8,7 @@ tuned against it yet (one 128 x 256 tile per CTA, no persistence, no 2-CTA pairs
 """
 from __future__ import annotations
 
+import os
 from ctypes import c_int, c_void_p
 from typing import Optional, Tuple
 
@@ -23,7 +24,7 @@ def _lib():
     global _bound
     lib = load_library()
     if not _bound:
-        lib.adapcc_gemm_bias_act.argtypes = [c_void_p] * 5 + [c_int] * 4 + [c_void_p]
+        lib.adapcc_gemm_bias_act_v.argtypes = [c_void_p] * 5 + [c_int] * 5 + [c_void_p]
         _bound = True
     return lib
 
@@ -33,8 +34,14 @@ def supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
             and weight.shape[1] % 64 == 0 and weight.shape[0] % 128 == 0)
 
 
+def default_variant() -> int:
+    """0: one output tile per CTA (validated on B200). 1: persistent CTAs with a double-buffered TMEM accumulator
+    (``ADAPCC_TCGEN05_VARIANT=1``; compiled and SASS-checked, first GPU run pending)."""
+    return int(os.environ.get("ADAPCC_TCGEN05_VARIANT", "0"))
+
+
 def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: str = "gelu",
-               save_pre: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+               save_pre: bool = False, variant: Optional[int] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """-> (act(x @ weight.T + bias), pre-activation or None). x [..., K], weight [N, K], bias [N]; bf16."""
     if not supported(x, weight):
         raise NativeError("linear_act: needs bf16 CUDA tensors with K % 64 == 0 and N % 128 == 0")
@@ -45,10 +52,11 @@ def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     out = torch.empty(m, n, dtype=torch.bfloat16, device=x.device)
     pre = torch.empty_like(out) if save_pre else None
     b = bias.contiguous() if bias is not None else None
-    rc = _lib().adapcc_gemm_bias_act(c_void_p(x2.data_ptr()), c_void_p(w.data_ptr()),
-                                     c_void_p(b.data_ptr() if b is not None else 0), c_void_p(out.data_ptr()),
-                                     c_void_p(pre.data_ptr() if pre is not None else 0), m, n, k, ACT[act],
-                                     c_void_p(torch.cuda.current_stream().cuda_stream))
+    rc = _lib().adapcc_gemm_bias_act_v(c_void_p(x2.data_ptr()), c_void_p(w.data_ptr()),
+                                       c_void_p(b.data_ptr() if b is not None else 0), c_void_p(out.data_ptr()),
+                                       c_void_p(pre.data_ptr() if pre is not None else 0), m, n, k, ACT[act],
+                                       default_variant() if variant is None else int(variant),
+                                       c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0:
         raise NativeError(f"gemm_bias_act failed: {last_error()}")
     shape = x.shape[:-1] + (n,)

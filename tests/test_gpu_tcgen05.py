@@ -1,9 +1,14 @@
 """tcgen05 GEMM with fused bias + GELU epilogue (csrc/gemm_tcgen05.cu) against a plain PyTorch fp32 reference.
 All cases pass on B200 (gpurun call of this round, log/gpu_tcgen05_test.log)."""
+import os
+
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+# variant 1 (persistent CTAs, double-buffered TMEM) has been compiled and SASS-checked but not run yet: a protocol
+# bug would trap the kernel and poison this process's CUDA context, so it only runs when asked for
+VARIANTS = [0, 1] if os.environ.get("ADAPCC_EXPERIMENTAL", "0") == "1" else [0]
 
 
 @pytest.fixture(scope="module")
@@ -14,15 +19,17 @@ def dev():
 
 
 @pytest.mark.parametrize("m,n,k,act", [(128, 256, 64, "none"), (256, 256, 128, "gelu"), (200, 384, 192, "gelu"),
-                                       (1024, 3072, 768, "gelu"), (384, 128, 3072, "none")])
-def test_gemm_bias_act_matches_fp32_reference(dev, m, n, k, act):
+                                       (1024, 3072, 768, "gelu"), (384, 128, 3072, "none"),
+                                       (8192, 3072, 768, "gelu")])
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_gemm_bias_act_matches_fp32_reference(dev, m, n, k, act, variant):
     from adapcc_b200.ops.gemm import linear_act
 
     torch.manual_seed(m + n + k)
     x = torch.randn(m, k, device=dev).bfloat16()
     w = (torch.randn(n, k, device=dev) / k ** 0.5).bfloat16()
     b = torch.randn(n, device=dev).bfloat16()
-    out, pre = linear_act(x, w, b, act, save_pre=True)
+    out, pre = linear_act(x, w, b, act, save_pre=True, variant=variant)
     torch.cuda.synchronize()
     u = x.float() @ w.float().t() + b.float()
     assert torch.allclose(pre.float(), u, atol=3e-2, rtol=2e-2), (pre.float() - u).abs().max()
