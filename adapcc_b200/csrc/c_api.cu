@@ -133,6 +133,11 @@ int adapcc_tree_relay_persistent(void* h, int n_buckets, const long long* counts
   return static_cast<CommContext*>(h)->tree_relay_persistent(n_buckets, counts, chunk_bytes, wire, op,
                                                              sorted_active(active, n_active), (cudaStream_t)stream);
 }
+// opt-in low-latency path (context created with ADAPCC_LL=1): all ranks, <= 32 KB
+int adapcc_allreduce_ll(void* h, const void* in, void* out, long long count, int dtype, int op, void* stream) {
+  return static_cast<CommContext*>(h)->allreduce_ll(in, out, count, dtype, op, (cudaStream_t)stream);
+}
+int adapcc_ctx_has_ll(void* h) { return static_cast<CommContext*>(h)->has_ll() ? 1 : 0; }
 int adapcc_skip_op(void* h, void* stream) { return static_cast<CommContext*>(h)->skip_op((cudaStream_t)stream); }
 int adapcc_ctx_check(void* h, void* stream) { return static_cast<CommContext*>(h)->check((cudaStream_t)stream); }
 int adapcc_ctx_host_barrier(void* h) {

@@ -3,6 +3,7 @@
 #include <algorithm>
 
 #include "kernels_direct.cuh"
+#include "kernels_ll.cuh"
 #include "kernels_pipelined.cuh"
 #include "kernels_tree.cuh"
 
@@ -13,7 +14,7 @@ constexpr size_t kPadBytes = 16384;                       // barrier pad region
 constexpr size_t kFlagOffset = kPadBytes;                 // chunk flags follow
 constexpr size_t kSigBytes = 65536;
 constexpr size_t kStateEpoch = 0, kStateTicket = 12288, kStateErr = 12292, kStateSeq = 12296,
-                 kStateBytes = 16384;
+                 kStateLLSeq = 12304, kStateBytes = 16384;
 static_assert(kMaxBlocks * kMaxRanks * 4 <= kStateTicket, "epoch table too small");
 static_assert(kMaxBlocks * kMaxRanks * 4 <= kPadBytes, "pad too small");
 static_assert(3 * kMaxBlocks * 8 + kFlagOffset <= 32768, "flag region too small");
@@ -109,6 +110,12 @@ int CommContext::init(const std::string& name, int rank, int world, int device, 
   if (heap_bytes) {
     if (symm_.alloc(heap_bytes, true, &heap_)) return -1;
   }
+  {
+    const char* ll = getenv("ADAPCC_LL");              // opt-in: every rank of the job must set it alike
+    if (ll && atoi(ll) > 0 && world > 1) {
+      if (symm_.alloc(kLLBufferBytes, false, &ll_)) return -1;
+    }
+  }
   CUDA_TRY(cudaMalloc(&d_state_, kStateBytes));
   CUDA_TRY(cudaMemset(d_state_, 0, kStateBytes));
   CUDA_TRY(cudaMalloc(&d_pipe_, sizeof(PipeState)));
@@ -128,6 +135,7 @@ void CommContext::destroy() {
   inited_ = false;
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
+  if (ll_.size) symm_.free(&ll_);
   symm_.free(&heap_);
   symm_.free(&staging_);
   symm_.free(&sig_);
@@ -210,6 +218,43 @@ int CommContext::pick_algo(int algo, long long wire_bytes, int op, int wire, boo
   if (w.zero_copy) return nvls_pref ? NVLS : TWO_SHOT;
   if (wire_bytes <= tun.one_shot_max_bytes) return ONE_SHOT;
   return nvls_pref ? NVLS : TWO_SHOT;
+}
+
+int CommContext::allreduce_ll(const void* in, void* out, long long count, int dtype, int op, cudaStream_t stream) {
+  if (!inited_) { set_error("context not initialised"); return -1; }
+  if (count <= 0) return skip_op(stream);
+  const size_t esize = dtype_size(dtype);
+  if (world_ == 1) {
+    if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, (size_t)count * esize, cudaMemcpyDeviceToDevice, stream));
+    return skip_op(stream);
+  }
+  if (!ll_.size) { set_error("allreduce_ll: no LL buffer (create the context with ADAPCC_LL=1)"); return -1; }
+  if ((size_t)count * esize > (size_t)kLLMaxBytes) { set_error("allreduce_ll: message larger than %d bytes", kLLMaxBytes); return -1; }
+  if (((uintptr_t)in | (uintptr_t)out) & 3) { set_error("allreduce_ll: tensors must be 4-byte aligned"); return -1; }
+  std::vector<int> all(world_);
+  for (int r = 0; r < world_; ++r) all[r] = r;
+  DevComm dc;
+  Window w = resolve(nullptr, nullptr, 0, false);
+  if (fill_comm(all, w, &dc)) return -1;
+  LLArgs a{};
+  for (int r = 0; r < world_; ++r) a.ll[r] = (char*)ll_.peers[r];
+  a.ll_seq = (unsigned long long*)(d_state_ + kStateLLSeq);
+  const float scale = (op == AVG) ? 1.f / (float)world_ : 1.f;
+  const long long words = ((long long)count * (long long)esize + 3) / 4, lines = (words + 1) / 2;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(8, (lines + 255) / 256));
+#define LL_LAUNCH(U)                                                                                         \
+  do {                                                                                                       \
+    if (op == MAX) allreduce_ll_kernel<U, MAX><<<blocks, 256, 0, stream>>>(dc, a, (const U*)in, (U*)out, count, scale); \
+    else allreduce_ll_kernel<U, SUM><<<blocks, 256, 0, stream>>>(dc, a, (const U*)in, (U*)out, count, scale); \
+  } while (0)
+  if (dtype == F32) LL_LAUNCH(float);
+  else if (dtype == BF16) LL_LAUNCH(__nv_bfloat16);
+  else if (dtype == F16) LL_LAUNCH(__half);
+  else { set_error("allreduce_ll: unsupported dtype %d", dtype); return -1; }
+#undef LL_LAUNCH
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
 }
 
 int CommContext::skip_op(cudaStream_t stream) {

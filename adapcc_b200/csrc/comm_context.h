@@ -60,6 +60,10 @@ class CommContext {
   // launches when a bucket does not fit the staging window.
   int tree_relay_persistent(int n_buckets, const long long* counts, const long long* chunk_bytes, int wire, int op,
                             const std::vector<int>& active, cudaStream_t stream);
+  // Low-latency one-shot all-reduce (kernels_ll.cuh): all ranks active, <= 32 KB, flag-in-data, no barrier.
+  // Only available when the context was created with ADAPCC_LL=1 (allocates the 2 MB LL buffer).
+  int allreduce_ll(const void* in, void* out, long long count, int dtype, int op, cudaStream_t stream);
+  bool has_ll() const { return ll_.size != 0; }
   int skip_op(cudaStream_t stream);
   // One-CTA device barrier among `active` (orders peer stores before peer loads across kernels).
   int device_barrier(const std::vector<int>& active, cudaStream_t stream);
@@ -93,7 +97,7 @@ class CommContext {
   int pick_algo(int algo, long long wire_bytes, int op, int wire, bool all_active, const Window& w);
 
   SymmContext symm_;
-  SymmBuffer staging_, heap_, sig_;
+  SymmBuffer staging_, heap_, sig_, ll_;
   char* d_state_ = nullptr;            // bar_epoch[], ticket, err, seq
   void* d_pipe_ = nullptr;             // PipeState of the pipelined staged kernel
   void* d_relay_work_ = nullptr;       // RelayWork[] scratch of the persistent relay kernel

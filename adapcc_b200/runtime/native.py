@@ -76,6 +76,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
                                                      ctypes.POINTER(c_longlong), c_int, c_int, ip, c_int, c_void_p]
         lib.adapcc_alltoall.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, ip, c_int, c_void_p]
         lib.adapcc_skip_op.argtypes = [c_void_p, c_void_p]
+        lib.adapcc_allreduce_ll.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]
+        lib.adapcc_ctx_has_ll.argtypes = [c_void_p]
         lib.adapcc_ctx_check.argtypes = [c_void_p, c_void_p]
         lib.adapcc_ctx_host_barrier.argtypes = [c_void_p]
         lib.adapcc_relay_control.argtypes = [c_char_p, c_int, c_int, c_int, ip, c_int, ip, c_int]
@@ -236,11 +238,27 @@ class NativeComm:
                    active=None, stream=None):
         out = tensor if out is None else out
         dt = self._dt(tensor)
+        if algo == "ll":
+            return self.all_reduce_ll(tensor, out=out, op=op, stream=stream)
         wd = dt if wire is None else DTYPE_IDS[wire]
         arr, n = self._active(active)
         _check(self.lib.adapcc_allreduce(self.handle, c_void_p(tensor.data_ptr()), c_void_p(out.data_ptr()),
                                          tensor.numel(), dt, wd, OP_IDS[op], ALGO_IDS[algo], arr, n,
                                          self._stream_ptr(stream)), "all_reduce")
+        return out
+
+    @property
+    def has_ll(self) -> bool:
+        return bool(self.lib.adapcc_ctx_has_ll(self.handle))
+
+    def all_reduce_ll(self, tensor, out=None, op: str = "sum", stream=None):
+        """Opt-in low-latency all-reduce (csrc/kernels_ll.cuh): every rank takes part, message <= 32 KB,
+        flag-in-data lines pushed into every peer's LL buffer — no barrier. The context must have been created
+        with ``ADAPCC_LL=1`` in the environment of every rank. Not yet validated on hardware."""
+        out = tensor if out is None else out
+        _check(self.lib.adapcc_allreduce_ll(self.handle, c_void_p(tensor.data_ptr()), c_void_p(out.data_ptr()),
+                                            tensor.numel(), self._dt(tensor), OP_IDS[op], self._stream_ptr(stream)),
+               "all_reduce_ll")
         return out
 
     def reduce(self, tensor, root: int, out=None, op: str = "sum", algo: str = "auto",

@@ -97,6 +97,26 @@ def main():
                     comm.check()
                     want = ref_reduce(world, n, dtype, seed, op, all_ranks, wire_t)
                     check(f"allreduce {algo} {dtype} wire={wire} {op} n={n}", x, want, dtype, wire_t, world)
+    # ---- opt-in low-latency path (ADAPCC_LL=1 in the environment of every rank) --------------------
+    if comm.has_ll:
+        for dtype in (torch.float32, torch.bfloat16, torch.float16):
+            for op in ("sum", "avg", "max"):
+                for n in (1, 2, 3, 255, 1024, 4097, 8192):           # <= 32 KB, odd tails included
+                    seed += 1
+                    x = gen(rank, n, dtype, seed).to(dev)
+                    comm.all_reduce(x, op=op, algo="ll")
+                    comm.check()
+                    check(f"allreduce ll {dtype} {op} n={n}", x, ref_reduce(world, n, dtype, seed, op, all_ranks),
+                          dtype, None, world)
+        # back-to-back ops without a host sync in between exercise the double-buffered slots; interleave a
+        # barrier-protocol op so both counters move
+        xs = [gen(rank, 1000 + i, torch.float32, 9000 + i).to(dev) for i in range(12)]
+        for i, x in enumerate(xs):
+            comm.all_reduce(x, op="sum", algo="ll" if i % 3 else "two_shot")
+        comm.check()
+        for i, x in enumerate(xs):
+            check(f"allreduce ll back-to-back {i}", x, ref_reduce(world, 1000 + i, torch.float32, 9000 + i, "sum",
+                                                                   all_ranks), torch.float32, None, world)
     # out-of-place + auto
     for n in sizes:
         seed += 1
@@ -372,6 +392,8 @@ def main():
                 row[algo] = timeit(lambda: comm.all_reduce(x, algo=algo), iters)
                 if hz is not None and algo not in ("one_shot",):
                     row[algo + "_zc"] = timeit(lambda: comm.all_reduce(hz, algo=algo), iters)
+            if comm.has_ll and nbytes <= 32768:
+                row["ll"] = timeit(lambda: comm.all_reduce(x, algo="ll"), iters)
             row["auto_eager"] = timeit(lambda: comm.all_reduce(x, algo="auto"), iters, graph=False)
             row["bf16wire_auto"] = timeit(lambda: comm.all_reduce(x, algo="auto", wire="bfloat16"), iters)
             if nbytes >= (1 << 16):
