@@ -2,10 +2,10 @@
 
     python -m adapcc_b200.bench.gemm_bench [--m 8192 --n 3072 --k 768] [--iters 50] [--json out.json]
 
-Each arm: warm-up, then ``iters`` launches between two CUDA events on the launching stream with an L2 flush
-(256 MB write) between timed batches is NOT needed here — inputs + outputs (A 12.6 MB, W 4.7 MB, out/pre 2 x 50 MB at
-the default shape) already exceed what stays resident across iterations together with the flush of the output
-write-back; the JSON records that choice. Reported: median of 5 batches, TFLOP/s = 2 M N K / t.
+Each arm: 5 warm-up calls, then 5 batches of ``iters`` back-to-back launches between two CUDA events on the
+launching stream; the median batch is reported as TFLOP/s = 2 M N K / t. No explicit L2 flush: at the default shape
+one call streams 70-120 MB (A 12.6 MB, W 4.7 MB, one or two 50 MB outputs), about the size of the 126 MB L2, so the
+outputs of one call evict the operands of the next; the JSON records this.
 """
 from __future__ import annotations
 
