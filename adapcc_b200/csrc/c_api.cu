@@ -62,6 +62,8 @@ void* adapcc_ctx_heap_ptr(void* h) { return static_cast<CommContext*>(h)->heap_p
 unsigned long long adapcc_ctx_heap_bytes(void* h) { return static_cast<CommContext*>(h)->heap_bytes(); }
 unsigned long long adapcc_ctx_staging_bytes(void* h) { return static_cast<CommContext*>(h)->staging_bytes(); }
 void* adapcc_ctx_peer_heap_ptr(void* h, int r) { return static_cast<CommContext*>(h)->peer_heap_ptr(r); }
+// multicast alias of the symmetric heap (NULL when no multicast object is bound)
+void* adapcc_ctx_heap_mc_ptr(void* h) { return static_cast<CommContext*>(h)->heap_mc_ptr(); }
 void* adapcc_ctx_peer_staging_ptr(void* h, int r) { return static_cast<CommContext*>(h)->peer_staging_ptr(r); }
 int adapcc_ctx_last_algo(void* h) { return static_cast<CommContext*>(h)->last_algo; }
 

@@ -86,6 +86,7 @@ class CommContext {
   void* peer_heap_ptr(int r) const { return heap_.peers[r]; }
   void* peer_staging_ptr(int r) const { return staging_.peers[r]; }
   void* staging_mc_ptr() const { return staging_.mc; }
+  void* heap_mc_ptr() const { return heap_.mc; }
   // 2*kMaxRanks u64 ping-pong slots of rank r (inside its signal window)
   void* profile_flag_ptr(int r) const { return (char*)sig_.peers[r] + 32768; }
 

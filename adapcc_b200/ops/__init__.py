@@ -27,6 +27,8 @@ def _lib():
         lib.adapcc_fused_sgd.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_float, c_float,
                                          c_void_p]
         lib.adapcc_incr_int.argtypes = [c_void_p, c_void_p]
+        lib.adapcc_zero_adamw_bcast.argtypes = [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p,
+                                                c_void_p, c_longlong] + [c_float] * 7 + [c_void_p, c_void_p, c_void_p]
         lib.adapcc_fused_ce.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
         _bound = True
     return lib
@@ -65,6 +67,33 @@ def fused_adamw_(param: torch.Tensor, grad: torch.Tensor, master: torch.Tensor, 
                                   c_void_p(sumsq.data_ptr() if sumsq is not None else None),
                                   c_void_p(step_tensor.data_ptr() if step_tensor is not None else None), _stream()),
         "fused_adamw")
+
+
+def zero_adamw_bcast_(comm, param_shard: torch.Tensor, grad_shard: torch.Tensor, master: torch.Tensor,
+                      m: torch.Tensor, v: torch.Tensor, *, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+                      weight_decay: float = 0.01, max_norm: float = 0.0, grad_scale: float = 1.0,
+                      sumsq: Optional[torch.Tensor] = None, step_tensor: torch.Tensor = None) -> None:
+    """ZeRO-1 step for one shard (csrc/zero.cu): AdamW on this rank's slice of the (symmetric-heap) parameter
+    buffer; the updated bf16 parameters are written through the heap's multicast alias (``multimem.st``: the switch
+    replicates them into every rank's copy) or, without multicast, stored into every peer's buffer. ``param_shard``
+    must be a view inside ``comm``'s symmetric heap; master / m / v are the shard's fp32 state. Opt-in path, first
+    GPU run pending."""
+    n = param_shard.numel()
+    if n == 0:
+        return
+    off = comm.heap_offset(param_shard)
+    mc = comm.heap_mc_ptr()
+    peers = None
+    npeers = 0
+    if not mc:
+        ptrs = [comm.peer_heap_ptr(r) for r in range(comm.world)]
+        peers = (c_void_p * len(ptrs))(*ptrs)
+        npeers = len(ptrs)
+    _ck(_lib().adapcc_zero_adamw_bcast(c_void_p(mc or None), peers, npeers, off, c_void_p(grad_shard.data_ptr()),
+                                       c_void_p(master.data_ptr()), c_void_p(m.data_ptr()), c_void_p(v.data_ptr()), n,
+                                       lr, betas[0], betas[1], eps, weight_decay, max_norm, grad_scale,
+                                       c_void_p(sumsq.data_ptr() if sumsq is not None else None),
+                                       c_void_p(step_tensor.data_ptr()), _stream()), "zero_adamw_bcast")
 
 
 def fused_sgd_(param, grad, master, *, lr: float, grad_scale: float = 1.0) -> None:

@@ -59,12 +59,16 @@ class FlatDataParallel:
                  bucket_mb: float = 32.0, lr: float = 6.25e-5, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.01, max_norm: float = 1.0, optimizer: str = "adamw",
                  param_dtype: torch.dtype = torch.bfloat16, algo: str = "auto", active: Optional[Sequence[int]] = None,
-                 comm_fn: Optional[Callable] = None, direct_grads: Optional[bool] = None):
+                 comm_fn: Optional[Callable] = None, direct_grads: Optional[bool] = None,
+                 zero1: Optional[bool] = None):
         """``comm``: a :class:`~adapcc_b200.runtime.native.NativeComm` (or None for one GPU).
         ``comm_fn(flat_slice)``: alternative collective (e.g. an NCCL all-reduce) for baselines.
         ``direct_grads``: FusedLinear / FusedLayerNorm backward kernels write their parameter gradients
         straight into the flat buffer (no per-parameter accumulate kernel). Requires every such module to
-        be applied once per step; default on (``ADAPCC_DIRECT_GRADS=0`` turns it off)."""
+        be applied once per step; default on (``ADAPCC_DIRECT_GRADS=0`` turns it off).
+        ``zero1`` (opt-in, ``ADAPCC_ZERO1=1``; first GPU run pending): shard the optimizer over the ranks — buckets
+        are reduce-SCATTERED during backward, every rank runs AdamW on its 1/N slices only and the updated
+        parameters are broadcast by the same kernel through the NVSwitch multicast alias (csrc/zero.cu)."""
         self.model, self.comm, self.world_size, self.rank = model, comm, world_size, rank
         self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
         self.optimizer, self.algo, self.comm_fn = optimizer, algo, comm_fn
@@ -76,8 +80,20 @@ class FlatDataParallel:
         self.total = total
         dev = self.device
         # ---- flat parameter / gradient / optimizer state ---------------------------------------
-        self.flat_param = torch.zeros(total, dtype=param_dtype, device=dev)
-        esize = self.flat_param.element_size()
+        esize = torch.empty((), dtype=param_dtype).element_size()
+        if zero1 is None:
+            zero1 = os.environ.get("ADAPCC_ZERO1", "0") == "1"
+        self.zero1 = bool(zero1 and comm is not None and world_size > 1 and comm_fn is None and optimizer == "adamw"
+                          and param_dtype == torch.bfloat16 and self.active == list(range(world_size))
+                          and comm.heap_bytes >= 2 * (total * esize + 4096))
+        if zero1 and world_size > 1 and not self.zero1:
+            raise ValueError("zero1 needs a native communicator whose symmetric heap holds parameters AND gradients "
+                             f"({2 * total * esize >> 20} MB), bf16 parameters, AdamW and all ranks active")
+        if self.zero1:
+            self.flat_param = comm.symm_empty(total, param_dtype)   # peers write their updated slices into it
+            self.flat_param.zero_()
+        else:
+            self.flat_param = torch.zeros(total, dtype=param_dtype, device=dev)
         self.zero_copy = False
         if comm is not None and world_size > 1 and comm.heap_bytes >= total * esize + 4096:
             self.flat_grad = comm.symm_empty(total, param_dtype)
@@ -116,6 +132,17 @@ class FlatDataParallel:
                     self._bucket_of[j] = len(self.buckets)
                 self.buckets.append(_Bucket(start, end, len(members)))
                 end, members = start, []
+        # ZeRO-1 slices: the direct kernels cut a message into world slices of ceil(packs / world) 16-byte
+        # packs (csrc/kernels_direct.cuh::Partition); rank r owns slice r of every bucket
+        self._my_slices: List[tuple] = []
+        if self.zero1:
+            epp = 16 // esize
+            for b in self.buckets:
+                packs = (b.end - b.start + epp - 1) // epp
+                pps = (packs + world_size - 1) // world_size
+                lo = min(packs, rank * pps) * epp
+                hi = min(packs, (rank + 1) * pps) * epp
+                self._my_slices.append((b.start + lo, min(b.end, b.start + hi)))
         self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(params)]
         if direct_grads is None:
             direct_grads = os.environ.get("ADAPCC_DIRECT_GRADS", "1") != "0"
@@ -165,6 +192,10 @@ class FlatDataParallel:
             seg = self.flat_grad[b.start:b.end]
             if self.comm_fn is not None:
                 self.comm_fn(seg)
+            elif self.zero1:
+                # reduce-scatter in place: the direct reduce kernel with root = self leaves the averaged
+                # slice `rank` of the bucket in this rank's buffer and moves 1/2 of an all-reduce's bytes
+                self.comm.reduce(seg, root=self.rank, op="avg", algo=self.algo, active=self.active)
             else:
                 self.comm.all_reduce(seg, op="avg", algo=self.algo, active=self.active)
 
@@ -185,7 +216,9 @@ class FlatDataParallel:
         if self._forked:                              # join the collective stream (also under capture)
             cur.wait_stream(self.comm_stream)
         incr_(self.step_t)
-        if self.optimizer == "adamw":
+        if self.zero1:
+            self._zero1_update()
+        elif self.optimizer == "adamw":
             sumsq = None
             if self.max_norm and self.max_norm > 0:
                 self.sumsq.zero_()
@@ -197,6 +230,27 @@ class FlatDataParallel:
         else:
             fused_sgd_(self.flat_param, self.flat_grad, self.master, lr=self.lr)
         return loss.detach()
+
+    def _zero1_update(self) -> None:
+        """Sharded optimizer step: norm of my slices -> 4-byte all-reduce -> AdamW on my slices with the parameter
+        broadcast fused into the kernel -> device barrier."""
+        from ..ops import sumsq_, zero_adamw_bcast_
+
+        clip = bool(self.max_norm and self.max_norm > 0)
+        self.sumsq.zero_()
+        if clip:
+            for lo, hi in self._my_slices:
+                if hi > lo:
+                    sumsq_(self.flat_grad[lo:hi], self.sumsq)
+        # also when not clipping: this all-reduce is the point after which no rank still reads the old parameters
+        self.comm.all_reduce(self.sumsq, op="sum", active=self.active)
+        for lo, hi in self._my_slices:
+            if hi > lo:
+                zero_adamw_bcast_(self.comm, self.flat_param[lo:hi], self.flat_grad[lo:hi], self.master[lo:hi],
+                                  self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], lr=self.lr, betas=self.betas,
+                                  eps=self.eps, weight_decay=self.weight_decay, max_norm=self.max_norm or 0.0,
+                                  sumsq=self.sumsq if clip else None, step_tensor=self.step_t)
+        self.comm.device_barrier(self.active)
 
     def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         """Eager step on device-resident inputs. Returns the (device) loss."""

@@ -54,6 +54,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
         lib.adapcc_ctx_heap_bytes.argtypes = [c_void_p]
         lib.adapcc_ctx_staging_bytes.restype = c_ulonglong
         lib.adapcc_ctx_staging_bytes.argtypes = [c_void_p]
+        lib.adapcc_ctx_heap_mc_ptr.restype = c_void_p
+        lib.adapcc_ctx_heap_mc_ptr.argtypes = [c_void_p]
         lib.adapcc_ctx_peer_heap_ptr.restype = c_void_p
         lib.adapcc_ctx_peer_heap_ptr.argtypes = [c_void_p, c_int]
         lib.adapcc_ctx_peer_staging_ptr.restype = c_void_p
@@ -76,6 +78,7 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
                                                      ctypes.POINTER(c_longlong), c_int, c_int, ip, c_int, c_void_p]
         lib.adapcc_alltoall.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, ip, c_int, c_void_p]
         lib.adapcc_skip_op.argtypes = [c_void_p, c_void_p]
+        lib.adapcc_barrier.argtypes = [c_void_p, ctypes.POINTER(c_int), c_int, c_void_p]
         lib.adapcc_allreduce_ll.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]
         lib.adapcc_ctx_has_ll.argtypes = [c_void_p]
         lib.adapcc_ctx_check.argtypes = [c_void_p, c_void_p]
@@ -212,6 +215,25 @@ class NativeComm:
             self._pool_allocator = alloc
             self._pool = torch.cuda.MemPool(alloc.allocator())
         return self._pool
+
+    def heap_offset(self, tensor) -> int:
+        """Byte offset of a heap tensor inside the symmetric heap (the same on every rank)."""
+        base = self.lib.adapcc_ctx_heap_ptr(self.handle) or 0
+        if not self.in_heap(tensor):
+            raise NativeError("tensor is not inside the symmetric heap")
+        return tensor.data_ptr() - base
+
+    def heap_mc_ptr(self) -> int:
+        """Multicast alias of the heap base (0 when no multicast object is bound)."""
+        return int(self.lib.adapcc_ctx_heap_mc_ptr(self.handle) or 0)
+
+    def peer_heap_ptr(self, r: int) -> int:
+        return int(self.lib.adapcc_ctx_peer_heap_ptr(self.handle, int(r)) or 0)
+
+    def device_barrier(self, active=None, stream=None) -> None:
+        """One-CTA device-side barrier among ``active`` on ``stream`` (orders peer stores before later kernels)."""
+        arr, n = self._active(active)
+        _check(self.lib.adapcc_barrier(self.handle, arr, n, self._stream_ptr(stream)), "device_barrier")
 
     def in_heap(self, tensor) -> bool:
         base = self.lib.adapcc_ctx_heap_ptr(self.handle) or 0

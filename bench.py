@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--lm_rows", default="all", choices=["all", "scored"],
                     help="all: LM head on every position (reference behaviour, the default and the judged "
                          "number); scored: only rows whose label is not -100 (same loss and gradients)")
+    ap.add_argument("--zero1", action="store_true",
+                    help="opt-in sharded optimizer: reduce-scatter + AdamW with the parameter broadcast fused "
+                         "(multimem.st); N > 1 only; not the judged default")
     ap.add_argument("--lm_chunk", type=int, default=0, help="rows per fused LM-head/CE chunk (0 = model default)")
     ap.add_argument("--tiny", action="store_true", help="tiny model (smoke tests only; never a bench value)")
     return ap.parse_args()
@@ -176,7 +179,7 @@ def main():
                            logical_graph=os.path.join(work, "topology", f"logical_graph_{world}.xml"),
                            entry_point=a.entry_point, parallel_degree=min(4, world), profile_freq=500,
                            work_dir=work, relay_control=False, algo=a.algo,
-                           heap_mb=(grad_bytes >> 20) + 64, staging_mb=64, backend="nccl")
+                           heap_mb=((2 if a.zero1 else 1) * grad_bytes >> 20) + 64, staging_mb=64, backend="nccl")
     comm = None
     comm_fn = None
     if a.impl == "adapcc":
@@ -231,7 +234,8 @@ def main():
         n_buckets, zero_copy = -1, (a.impl == "adapcc" and world > 1)
     else:
         engine = FlatDataParallel(model, comm, world_size=world, rank=rank, bucket_mb=a.bucket_mb, lr=6.25e-5,
-                                  max_norm=1.0, algo=a.algo, comm_fn=comm_fn)
+                                  max_norm=1.0, algo=a.algo, comm_fn=comm_fn,
+                                  zero1=(a.zero1 and world > 1 and comm is not None) or None)
         n_buckets, zero_copy = len(engine.buckets), engine.zero_copy
         if use_graph:
             engine.capture(dev_batch, warmup=2)
@@ -297,7 +301,8 @@ def main():
                        "global_batch": a.batch * world, "per_gpu_batch": a.batch, "candidates": a.candidates,
                        "seq_len": seq, "parallelism": f"dp{world}", "engine": a.engine, "algo": a.algo,
                        "optimizer": "adamw+clip1.0 (fused)", "grad_dtype": "bf16", "zero_copy_grads": zero_copy,
-                       "buckets": n_buckets, "lm_rows": a.lm_rows, "lm_chunk_rows": cfg.lm_chunk_rows,
+                       "buckets": n_buckets, "zero1": bool(engine is not None and getattr(engine, "zero1", False)),
+                       "lm_rows": a.lm_rows, "lm_chunk_rows": cfg.lm_chunk_rows,
                        "fuse_add_ln": bool(getattr(model, "fuse_add_ln", False)),
                        "l2": "working set (params+grads+optimizer state ~2 GB/step) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": tokens_per_step / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e,

@@ -26,3 +26,19 @@ def test_collectives_multi_gpu():
     tail = (r.stdout + r.stderr)[-4000:]
     assert r.returncode == 0, tail
     assert "failures: 0" in r.stdout, tail
+
+
+@pytest.mark.skipif(os.environ.get("ADAPCC_EXPERIMENTAL", "0") != "1",
+                    reason="sharded-optimizer mode has not had its first GPU run: set ADAPCC_EXPERIMENTAL=1")
+def test_zero1_engine_matches_data_parallel():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 4 if n >= 4 else 2
+    env = dict(os.environ, ADAPCC_TIMEOUT_MS="15000")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tests", "gpu_zero1_worker.py")]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    tail = (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0, tail
+    assert "failures: 0" in r.stdout, tail
