@@ -7,7 +7,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from adapcc_b200.ops.layers import FusedLayerNorm, FusedLinear  # noqa: E402
+from adapcc_b200.ops.layers import FusedLinear  # noqa: E402
 
 dev = torch.device("cuda", 0)
 B, T, D, H = 8, 1024, 768, 12

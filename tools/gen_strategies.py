@@ -7,8 +7,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from adapcc_b200.strategy import make_strategy, xmlio  # noqa: E402
-from adapcc_b200.synth import LinkModel, ParTrees, Solver  # noqa: E402
+from adapcc_b200.strategy import make_strategy  # noqa: E402
+from adapcc_b200.synth import ParTrees, Solver  # noqa: E402
 from adapcc_b200.topology import local_rank0_list  # noqa: E402
 
 
