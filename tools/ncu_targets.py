@@ -50,6 +50,19 @@ def main():
         xx = torch.randn(8192, 768, device=dev).bfloat16().requires_grad_(True)
         for _ in range(3):
             ln(xx).backward(torch.randn(8192, 768, device=dev).bfloat16())
+    if which in ("all", "gemm"):
+        # the tcgen05 GEMM at the GPT-2 MLP up-projection shape, both variants
+        # (ncu -k regex:gemm_bias_act_tcgen05 --set full ... python tools/ncu_targets.py gemm [variants, e.g. 0,1])
+        from adapcc_b200.ops.gemm import linear_act
+        variants = [int(t) for t in (sys.argv[2] if len(sys.argv) > 2 else "0").split(",")]
+        a = torch.randn(8192, 768, device=dev).bfloat16()
+        w = (torch.randn(3072, 768, device=dev) / 28).bfloat16()
+        b = torch.randn(3072, device=dev).bfloat16()
+        for v in variants:
+            for _ in range(3):
+                linear_act(a, w, b, "gelu", save_pre=True, variant=v)
+        for _ in range(3):                                           # the cuBLAS kernels it competes with
+            torch.nn.functional.gelu(torch.nn.functional.linear(a, w, b), approximate="tanh")
     torch.cuda.synchronize()
 
 
