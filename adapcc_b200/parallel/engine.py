@@ -35,6 +35,17 @@ class _Bucket:
     pending: int = 0
 
 
+def shard_of(start: int, end: int, rank: int, world: int, elems_per_pack: int) -> tuple:
+    """Element range [lo, hi) of ``rank``'s slice of the message [start, end) under the direct kernels' partition
+    (csrc/kernels_direct.cuh::Partition): the message is cut into 16-byte packs, ``world`` contiguous slices of
+    ceil(packs / world) packs each, slice r owned by rank r (trailing slices may be short or empty)."""
+    packs = (end - start + elems_per_pack - 1) // elems_per_pack
+    pps = (packs + world - 1) // world
+    lo = min(packs, rank * pps) * elems_per_pack
+    hi = min(packs, (rank + 1) * pps) * elems_per_pack
+    return start + lo, min(end, start + hi)
+
+
 class _GradSink:
     """Handed to the fused ops (ops/layers.py::_sink) through ``param._adapcc_grad_sink``: the op writes
     the parameter's gradient straight into its view of the flat buffer and reports it here."""
@@ -136,13 +147,7 @@ class FlatDataParallel:
         # packs (csrc/kernels_direct.cuh::Partition); rank r owns slice r of every bucket
         self._my_slices: List[tuple] = []
         if self.zero1:
-            epp = 16 // esize
-            for b in self.buckets:
-                packs = (b.end - b.start + epp - 1) // epp
-                pps = (packs + world_size - 1) // world_size
-                lo = min(packs, rank * pps) * epp
-                hi = min(packs, (rank + 1) * pps) * epp
-                self._my_slices.append((b.start + lo, min(b.end, b.start + hi)))
+            self._my_slices = [shard_of(b.start, b.end, rank, world_size, 16 // esize) for b in self.buckets]
         self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(params)]
         if direct_grads is None:
             direct_grads = os.environ.get("ADAPCC_DIRECT_GRADS", "1") != "0"

@@ -53,3 +53,43 @@ def test_vit_steps_on_cpu():
     assert out.shape == (2, vit.cfg.num_classes)
     out.sum().backward()
     assert all(p.grad is not None for p in vit.parameters())
+
+
+def test_zero1_shards_tile_every_bucket_like_the_kernel_partition():
+    from adapcc_b200.parallel.engine import shard_of
+
+    for start, end in ((0, 8), (64, 64 + 8 * 1001), (8, 8 + 8 * 7), (0, 8 * 64)):
+        for world in (2, 3, 4, 8):
+            shards = [shard_of(start, end, r, world, 8) for r in range(world)]
+            assert shards[0][0] == start and max(hi for _, hi in shards) == end
+            pos = start
+            for lo, hi in shards:                      # contiguous, ordered, 16-byte aligned, no overlap
+                assert lo == min(pos, end) and hi >= lo and (lo - start) % 8 == 0
+                pos = hi if hi > lo else pos
+            # same formula as Partition::slice_begin / slice_count, in packs
+            packs = (end - start) // 8
+            pps = -(-packs // world)
+            for r, (lo, hi) in enumerate(shards):
+                assert (hi - lo) // 8 == max(0, min(pps, packs - r * pps))
+
+
+def test_grad_sink_rejects_a_second_gradient_in_one_step():
+    import pytest
+
+    from adapcc_b200.parallel.engine import _GradSink
+
+    class _Eng:
+        ready = []
+
+        def _grad_ready(self, i):
+            self.ready.append(i)
+
+    eng = _Eng()
+    sink = _GradSink(eng, 3)
+    assert sink.begin() is True
+    sink.done()
+    assert eng.ready == [3]
+    with pytest.raises(RuntimeError, match="second gradient"):
+        sink.begin()
+    sink.written = False                                # the engine resets sinks at the start of a step
+    assert sink.begin() is True
