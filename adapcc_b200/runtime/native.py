@@ -294,6 +294,16 @@ class NativeComm:
                                       self._stream_ptr(stream)), "reduce")
         return out
 
+    def reduce_scatter_(self, tensor, op: str = "sum", algo: str = "auto", stream=None):
+        """In-place reduce-scatter over all ranks: afterwards elements ``[lo, hi)`` of ``tensor`` (the returned
+        range, this rank's slice under the direct kernels' partition) hold the reduction; the rest of the tensor
+        is unspecified. It is the direct reduce kernel with root = self, so it moves half the bytes of an
+        all-reduce. (Used by the engine's sharded-optimizer mode; first GPU run pending.)"""
+        from ..parallel.engine import shard_of
+
+        self.reduce(tensor, root=self.rank, op=op, algo=algo, stream=stream)
+        return shard_of(0, tensor.numel(), self.rank, self.world, 16 // tensor.element_size())
+
     def broadcast(self, tensor, root: int, active=None, stream=None):
         arr, n = self._active(active)
         _check(self.lib.adapcc_broadcast(self.handle, c_void_p(tensor.data_ptr()), tensor.numel(),

@@ -97,6 +97,27 @@ def main():
                     comm.check()
                     want = ref_reduce(world, n, dtype, seed, op, all_ranks, wire_t)
                     check(f"allreduce {algo} {dtype} wire={wire} {op} n={n}", x, want, dtype, wire_t, world)
+    # ---- reduce-scatter = reduce with root = self (opt-in until its first GPU run) ---------------------
+    if os.environ.get("ADAPCC_EXPERIMENTAL", "0") == "1":
+        for dtype in (torch.float32, torch.bfloat16):
+            for algo in algos:
+                if algo == "one_shot":
+                    continue
+                for n in (4097, (1 << 20) + 3):
+                    seed += 1
+                    for zc in (False, True):
+                        if zc:
+                            comm.heap_reset()
+                            x = comm.symm_empty(n, dtype)
+                            x.copy_(gen(rank, n, dtype, seed).to(dev))
+                            dist.barrier()
+                        else:
+                            x = gen(rank, n, dtype, seed).to(dev)
+                        lo, hi = comm.reduce_scatter_(x, op="sum", algo=algo)
+                        comm.check()
+                        want = ref_reduce(world, n, dtype, seed, "sum", all_ranks)
+                        check(f"reduce_scatter {algo} {dtype} n={n} zc={zc} shard=[{lo},{hi})", x[lo:hi], want[lo:hi],
+                              dtype, None, world)
     # ---- opt-in low-latency path (ADAPCC_LL=1 in the environment of every rank) --------------------
     if comm.has_ll:
         for dtype in (torch.float32, torch.bfloat16, torch.float16):
