@@ -30,7 +30,7 @@ class AdapCC:
     def init(cls, args, local_rank, world_rank, world_size):
         """Create the communicator and run the workflow stages ``args.entry_point`` asks for: 6 = DETECT
         (topology -> logical graph) then PROFILE (link microbench -> synthesised strategy XML), 7 = PROFILE only,
-        -1 = keep ``args.strategy_file``. Collective over all ranks (reference: adapcc.py:17-41)."""
+        -1 = keep ``args.strategy_file``. Collective over all ranks (reference: /root/reference/adapcc.py:16-42)."""
         dylib = None
         if getattr(args, "backend", "nccl") != "gloo":
             try:
@@ -64,24 +64,24 @@ class AdapCC:
     @classmethod
     def setup(cls, prim):
         """Build the data-plane context for ``prim`` (ALLREDUCE / REDUCE / BOARDCAST / ALLTOALL): symmetric buffers,
-        strategy tables, coordinator + controller when relay control is on (reference: adapcc.py:43-45)."""
+        strategy tables, coordinator + controller when relay control is on (reference: /root/reference/adapcc.py:44-46)."""
         cls.communicator.init_threads(prim)
 
     @classmethod
     def allreduce(cls, tensor, size=None, chunk_bytes=None, active_gpus=None):
         """In-place all-reduce (sum) of the first ``size`` elements of ``tensor`` over ``active_gpus`` (default: all),
-        asynchronous on the current stream; returns the tensor (reference: adapcc.py:47-49)."""
+        asynchronous on the current stream; returns the tensor (reference: /root/reference/adapcc.py:48-50)."""
         return cls.communicator.all_reduce(tensor, size, chunk_bytes, active_gpus)
 
     @classmethod
     def reduce(cls, tensor, size=None, chunk_bytes=None, active_gpus=None):
         """In-place reduce: every strategy tree's root ends up with the sum of its slice (direct algorithms: rank 0
-        holds the whole result) — reference semantics, adapcc.py:51-53."""
+        holds the whole result) — reference semantics, /root/reference/adapcc.py:52-54."""
         return cls.communicator.reduce(tensor, size, chunk_bytes, active_gpus)
 
     @classmethod
     def boardcast(cls, tensor, size=None, chunk_bytes=None):
-        """Broadcast (the reference's spelling): every rank receives the roots' data (reference: adapcc.py:55-57)."""
+        """Broadcast (the reference's spelling): every rank receives the roots' data (reference: /root/reference/adapcc.py:56-58)."""
         return cls.communicator.boardcast(tensor, size, chunk_bytes)
 
     @classmethod
@@ -96,7 +96,7 @@ class AdapCC:
     @classmethod
     def reconstruct_topology(cls, args, prim):
         """Re-run init (re-profile / re-synthesise per ``args.entry_point``) and rebuild the context for ``prim``; call
-        it every ``profile_freq`` steps from the training loop (reference: adapcc.py:63-68)."""
+        it every ``profile_freq`` steps from the training loop (reference: /root/reference/adapcc.py:64-68)."""
         cls.clear(prim)
         cls.init(args, cls.local_rank, cls.world_rank, cls.world_size)
         cls.setup(prim)
@@ -108,6 +108,6 @@ class AdapCC:
 
     @classmethod
     def clear(cls, prim):
-        """Tear down the context for ``prim`` and the control plane (collective; reference: adapcc.py:73-76)."""
+        """Tear down the context for ``prim`` and the control plane (collective; reference: /root/reference/adapcc.py:74-76)."""
         cls.communicator.exit_threads(prim)
         cls.communicator.clear()

@@ -315,7 +315,7 @@ class CudaCommu:
     def init_threads(self, prim):
         """Enter a workflow stage or build a data-plane context: DETECT (native topology discovery), PROFILE (link
         micro-benchmarks), or a collective primitive (load the strategy, create the native context).
-        Reference: commu.py:120-180 (``initThreads`` in csrc/run.cu:19-60)."""
+        Reference: /root/reference/commu.py:301-319."""
         if prim == DETECT:
             self._detect()
         elif prim == PROFILE:
@@ -336,7 +336,7 @@ class CudaCommu:
     def exit_threads(self, prim):
         """Leave a stage: DETECT gathers the per-server files into the logical graph, PROFILE gathers the link
         records and synthesises the strategy (rank 0) and distributes it, a primitive closes its context.
-        Reference: commu.py:182-240."""
+        Reference: /root/reference/commu.py:321-358."""
         if prim == DETECT:
             if self.local_rank == 0:
                 self.dispatcher.dispatch_detected_topo(os.path.join(self.topo_dir, "topo_detect*"), self.topo_dir)
@@ -647,7 +647,7 @@ class CudaCommu:
     # @buffer: torch tensor (device or host), @size: number of elements, @chunk_bytes: pipelining
     # granularity in bytes, @active_gpus: world ranks taking part (reference signature).
     def all_reduce(self, buffer, size=None, chunk_bytes=None, active_gpus=None, op="sum"):
-        """In-place all-reduce of ``buffer[:size]`` over ``active_gpus`` (reference signature, commu.py:260-300);
+        """In-place all-reduce of ``buffer[:size]`` over ``active_gpus`` (reference signature, /root/reference/commu.py:360-365);
         ``op``: sum | avg | max. Asynchronous on the current CUDA stream; host tensors go through the CPU executor."""
         return self._collective(ALLREDUCE, buffer, size, chunk_bytes, active_gpus, op)
 
@@ -677,7 +677,7 @@ class CudaCommu:
         """torch DDP communication hook (``ddp.register_comm_hook(None, communicator.cuda_allreduce_hook)``): the first
         bucket of a step negotiates the active set with the coordinator (relay control), every bucket is reduced on a
         side stream by our kernels and returned as a CUDA future — unlike the reference's blocking hook
-        (commu.py:385-435), backward keeps running."""
+        (/root/reference/commu.py:385-435), backward keeps running."""
         import torch
 
         if self.local_hook_num == 0 and self.relay_control:
