@@ -103,6 +103,16 @@ fused_ce_smem_kernel(__nv_bfloat16* __restrict__ logits, const long long* __rest
   __shared__ float red[16];
   __shared__ float bcast[2];
 
+  if (!valid) {
+    // ignored row (label -100): loss 0, gradient exactly 0 — nothing to read, no exponentials; the row is only
+    // overwritten with zeros for the backward GEMMs. PersonaChat-shaped batches ignore 7 of 8 rows.
+    // (`valid` is uniform over the CTA, so the whole block leaves before the first barrier.)
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) st16(reinterpret_cast<uint4*>(p) + v, z);
+    if (threadIdx.x == 0) row_loss[row] = 0.f;
+    return;
+  }
+
   float m = -INFINITY;
   for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
     uint4 q = ld16(reinterpret_cast<const uint4*>(p) + v);
