@@ -304,6 +304,21 @@ class NativeComm:
         self.reduce(tensor, root=self.rank, op=op, algo=algo, stream=stream)
         return shard_of(0, tensor.numel(), self.rank, self.world, 16 // tensor.element_size())
 
+    def all_gather_(self, tensor, stream=None):
+        """In-place all-gather, the inverse of :meth:`reduce_scatter_`: on entry rank r's shard of ``tensor`` is valid,
+        on exit every rank holds every shard. Composed of one direct broadcast per shard (``world`` launches of the
+        validated broadcast kernel — multimem.st when multicast is bound); a single-kernel version is only worth
+        writing where this shows up in a profile (the sharded optimizer broadcasts from inside its own kernel)."""
+        from ..parallel.engine import shard_of
+
+        epp = 16 // tensor.element_size()
+        flat = tensor.view(-1)
+        for r in range(self.world):
+            lo, hi = shard_of(0, flat.numel(), r, self.world, epp)
+            if hi > lo:
+                self.broadcast(flat[lo:hi], root=r, stream=stream)
+        return tensor
+
     def broadcast(self, tensor, root: int, active=None, stream=None):
         arr, n = self._active(active)
         _check(self.lib.adapcc_broadcast(self.handle, c_void_p(tensor.data_ptr()), tensor.numel(),

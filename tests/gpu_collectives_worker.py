@@ -118,6 +118,10 @@ def main():
                         want = ref_reduce(world, n, dtype, seed, "sum", all_ranks)
                         check(f"reduce_scatter {algo} {dtype} n={n} zc={zc} shard=[{lo},{hi})", x[lo:hi], want[lo:hi],
                               dtype, None, world)
+                        comm.all_gather_(x)                 # reduce-scatter + all-gather == all-reduce
+                        comm.check()
+                        check(f"all_gather after reduce_scatter {algo} {dtype} n={n} zc={zc}", x, want, dtype, None,
+                              world)
     # ---- opt-in low-latency path (ADAPCC_LL=1 in the environment of every rank) --------------------
     if comm.has_ll:
         for dtype in (torch.float32, torch.bfloat16, torch.float16):
