@@ -159,6 +159,14 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return __fdividef(x, 1.f + __expf(-2.f * u));
 }
 
+// d/dx of the tanh-form GELU above: s + x s (1 - s) 2k (1 + 3c x^2), s = sigmoid(2u)
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float k = 0.7978845608028654f, c = 0.044715f;
+  const float u = k * (x + c * x * x * x);
+  const float sg = __fdividef(1.f, 1.f + __expf(-2.f * u));
+  return sg + x * sg * (1.f - sg) * 2.f * k * (1.f + 3.f * c * x * x);
+}
+
 template <int BN>
 struct Smem {
   static constexpr uint32_t kABytes = kBM * kBK * 2;            // 16 KB
@@ -169,7 +177,11 @@ struct Smem {
   static constexpr uint32_t kDynamic = kTotal + 1024;            // slack for the manual 1024-B alignment
 };
 
-// ACT: 0 = identity, 1 = GELU(tanh)
+// ACT: 0 = identity, 1 = GELU(tanh)                      -> out = act(acc + bias), optional pre = acc + bias
+//      2 = dGELU   : out = acc * gelu'(aux)               (backward of the MLP: dY.W2 with the activation's derivative
+//                                                          applied in the epilogue; aux = saved pre-activation)
+//      3 = residual: out = acc + bias + aux               (projection + residual add)
+// For ACT >= 2 the `pre` argument is an INPUT (aux, same shape as out) and nothing is written to it.
 template <int BN, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bias_act_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
@@ -269,6 +281,38 @@ gemm_bias_act_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
         for (int i = 0; i < 32; ++i) bf[i] = 0.f;
       }
       uint32_t packed_out[16], packed_pre[16];
+      if (ACT >= 2) {
+        // aux tile: this thread's 32 bf16 of the same row / columns (64 contiguous bytes)
+        uint32_t ax[16];
+        if (row < M) {
+          const uint4* ap = reinterpret_cast<const uint4*>(pre + row_off + c * 32);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint4 t = __ldg(ap + v);
+            ax[4 * v] = t.x; ax[4 * v + 1] = t.y; ax[4 * v + 2] = t.z; ax[4 * v + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ax[i] = 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ax[i]));
+          float o0, o1;
+          if (ACT == 2) {
+            o0 = __uint_as_float(acc[2 * i]) * gelu_tanh_grad(a2.x);
+            o1 = __uint_as_float(acc[2 * i + 1]) * gelu_tanh_grad(a2.y);
+          } else {
+            // bf16-round the projection first, then add: what `x + linear(h)` computes on bf16 tensors
+            const float2 pr = __bfloat1622float2(__floats2bfloat162_rn(__uint_as_float(acc[2 * i]) + bf[2 * i],
+                                                                       __uint_as_float(acc[2 * i + 1]) + bf[2 * i + 1]));
+            o0 = pr.x + a2.x;
+            o1 = pr.y + a2.y;
+          }
+          __nv_bfloat162 po = __floats2bfloat162_rn(o0, o1);
+          packed_out[i] = *reinterpret_cast<uint32_t*>(&po);
+        }
+      } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float u0 = __uint_as_float(acc[2 * i]) + bf[2 * i];
@@ -284,12 +328,13 @@ gemm_bias_act_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
           packed_out[i] = packed_pre[i];
         }
       }
+      }
       if (row < M) {
         uint4* o = reinterpret_cast<uint4*>(out + row_off + c * 32);
 #pragma unroll
         for (int v = 0; v < 4; ++v)
           o[v] = make_uint4(packed_out[4 * v], packed_out[4 * v + 1], packed_out[4 * v + 2], packed_out[4 * v + 3]);
-        if (pre != nullptr) {
+        if (ACT < 2 && pre != nullptr) {
           uint4* p = reinterpret_cast<uint4*>(pre + row_off + c * 32);
 #pragma unroll
           for (int v = 0; v < 4; ++v)
@@ -575,6 +620,7 @@ using namespace adapcc;
 extern "C" {
 
 // out = act(a[M,K] @ w[N,K]^T + bias); pre (optional) = the pre-activation. bf16 row-major, 16-byte aligned.
+// act 2: out = (a @ w^T) * gelu'(aux); act 3: out = a @ w^T + bias + aux — aux is passed in `pre` (an input then).
 // Constraints of this first version: K % 64 == 0, N % 128 == 0 (256-wide tiles when N % 256 == 0).
 // variant 0: one tile per CTA (validated on B200). variant 1: persistent CTAs, double-buffered TMEM accumulator
 // (compiled only so far).
@@ -582,7 +628,9 @@ int adapcc_gemm_bias_act_v(const void* a, const void* w, const void* bias, void*
                            int act, int variant, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (K % tc::kBK != 0 || N % 128 != 0) { set_error("gemm_tcgen05: need K %% 64 == 0 and N %% 128 == 0 (got K=%d N=%d)", K, N); return -1; }
-  if (act != 0 && act != 1) { set_error("gemm_tcgen05: act must be 0 (none) or 1 (gelu_tanh)"); return -1; }
+  if (act < 0 || act > 3) { set_error("gemm_tcgen05: act must be 0 (none), 1 (gelu_tanh), 2 (dgelu * aux) or 3 (+ aux)"); return -1; }
+  if (act >= 2 && pre == nullptr) { set_error("gemm_tcgen05: act %d needs the aux tensor (passed as `pre`)", act); return -1; }
+  if (act >= 2 && variant != 0) { set_error("gemm_tcgen05: act %d is only built for variant 0", act); return -1; }
   if (variant != 0 && variant != 1) { set_error("gemm_tcgen05: variant must be 0 or 1"); return -1; }
   if (((uintptr_t)a | (uintptr_t)w | (uintptr_t)out | (uintptr_t)pre | (uintptr_t)bias) & 15) { set_error("gemm_tcgen05: operands must be 16-byte aligned"); return -1; }
   const int bn = (N % 256 == 0) ? 256 : 128;
@@ -594,8 +642,16 @@ int adapcc_gemm_bias_act_v(const void* a, const void* w, const void* bias, void*
     if (bn == 256) return act ? tc::launch_persistent<256, 1>(ma, mw, bias, out, pre, M, N, K, s) : tc::launch_persistent<256, 0>(ma, mw, bias, out, pre, M, N, K, s);
     return act ? tc::launch_persistent<128, 1>(ma, mw, bias, out, pre, M, N, K, s) : tc::launch_persistent<128, 0>(ma, mw, bias, out, pre, M, N, K, s);
   }
-  if (bn == 256) return act ? tc::launch<256, 1>(ma, mw, bias, out, pre, M, N, K, s) : tc::launch<256, 0>(ma, mw, bias, out, pre, M, N, K, s);
-  return act ? tc::launch<128, 1>(ma, mw, bias, out, pre, M, N, K, s) : tc::launch<128, 0>(ma, mw, bias, out, pre, M, N, K, s);
+#define TC_LAUNCH(BN_)                                                                  \
+  switch (act) {                                                                        \
+    case 0: return tc::launch<BN_, 0>(ma, mw, bias, out, pre, M, N, K, s);              \
+    case 1: return tc::launch<BN_, 1>(ma, mw, bias, out, pre, M, N, K, s);              \
+    case 2: return tc::launch<BN_, 2>(ma, mw, bias, out, pre, M, N, K, s);              \
+    default: return tc::launch<BN_, 3>(ma, mw, bias, out, pre, M, N, K, s);             \
+  }
+  if (bn == 256) { TC_LAUNCH(256) }
+  TC_LAUNCH(128)
+#undef TC_LAUNCH
 }
 
 int adapcc_gemm_bias_act(const void* a, const void* w, const void* bias, void* out, void* pre, int M, int N, int K,

@@ -61,12 +61,15 @@ class Block(nn.Module):
         self.c_fc = FusedLinear(d, 4 * d)
         self.c_proj2 = FusedLinear(4 * d, d)
         # experimental: c_fc + bias + GELU as ONE tcgen05 GEMM (ops/gemm.py); off unless asked for
-        self.tc_mlp = os.environ.get("ADAPCC_TCGEN05_MLP", "0") == "1"
+        # 1: forward fusion only (validated kernel); 2: also dGELU in the backward GEMM's epilogue (first run pending)
+        self.tc_mlp = int(os.environ.get("ADAPCC_TCGEN05_MLP", "0") or 0)
 
     def _mlp(self, h: torch.Tensor) -> torch.Tensor:
         if self.tc_mlp and h.is_cuda and h.dtype == torch.bfloat16 and torch.is_grad_enabled():
-            from ..ops.gemm import linear_gelu, supported
+            from ..ops.gemm import linear_gelu, mlp_gelu, supported
             if supported(h, self.c_fc.weight):
+                if self.tc_mlp >= 2 and self.c_fc.weight.shape[0] % 64 == 0:
+                    return mlp_gelu(h, self.c_fc.weight, self.c_fc.bias, self.c_proj2.weight, self.c_proj2.bias)
                 return self.c_proj2(linear_gelu(h, self.c_fc.weight, self.c_fc.bias))
         return self.c_proj2(F.gelu(self.c_fc(h), approximate="tanh"))
 

@@ -17,7 +17,7 @@ import torch
 from ..runtime.native import NativeError, last_error, load_library
 
 _bound = False
-ACT = {"none": 0, "gelu": 1}
+ACT = {"none": 0, "gelu": 1, "dgelu": 2, "residual": 3}
 
 
 def _lib():
@@ -41,26 +41,40 @@ def default_variant() -> int:
 
 
 def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: str = "gelu",
-               save_pre: bool = False, variant: Optional[int] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """-> (act(x @ weight.T + bias), pre-activation or None). x [..., K], weight [N, K], bias [N]; bf16."""
+               save_pre: bool = False, variant: Optional[int] = None,
+               aux: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """-> (result, pre-activation or None). x [..., K], weight [N, K], bias [N]; bf16.
+
+    act "none" / "gelu": result = act(x @ weight.T + bias), optionally also the pre-activation (validated on B200).
+    act "dgelu":    result = (x @ weight.T) * gelu'(aux)      — the MLP backward with the activation's derivative in
+                    the epilogue (aux = the saved pre-activation, same shape as the result).
+    act "residual": result = x @ weight.T + bias + aux        — projection with the residual add in the epilogue.
+    (The two aux modes are compiled and SASS-checked; first GPU run pending.)"""
     if not supported(x, weight):
         raise NativeError("linear_act: needs bf16 CUDA tensors with K % 64 == 0 and N % 128 == 0")
     n, k = weight.shape
     x2 = x.reshape(-1, k).contiguous()
     w = weight.contiguous()
     m = x2.shape[0]
+    code = ACT[act]
     out = torch.empty(m, n, dtype=torch.bfloat16, device=x.device)
-    pre = torch.empty_like(out) if save_pre else None
+    if code >= 2:
+        if aux is None or aux.numel() != m * n or aux.dtype != torch.bfloat16:
+            raise NativeError(f"linear_act({act}): aux must be a bf16 tensor with the result's shape")
+        pre = aux.reshape(m, n).contiguous()            # an INPUT in these modes
+        v = 0                                           # only built for the per-tile variant
+    else:
+        pre = torch.empty_like(out) if save_pre else None
+        v = default_variant() if variant is None else int(variant)
     b = bias.contiguous() if bias is not None else None
     rc = _lib().adapcc_gemm_bias_act_v(c_void_p(x2.data_ptr()), c_void_p(w.data_ptr()),
                                        c_void_p(b.data_ptr() if b is not None else 0), c_void_p(out.data_ptr()),
-                                       c_void_p(pre.data_ptr() if pre is not None else 0), m, n, k, ACT[act],
-                                       default_variant() if variant is None else int(variant),
+                                       c_void_p(pre.data_ptr() if pre is not None else 0), m, n, k, code, v,
                                        c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0:
         raise NativeError(f"gemm_bias_act failed: {last_error()}")
     shape = x.shape[:-1] + (n,)
-    return out.view(shape), (pre.view(shape) if pre is not None else None)
+    return out.view(shape), (pre.view(shape) if (pre is not None and code < 2) else None)
 
 
 class _LinearGeluFn(torch.autograd.Function):
@@ -82,3 +96,33 @@ class _LinearGeluFn(torch.autograd.Function):
 def linear_gelu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """gelu_tanh(x @ weight.T + bias) with the bias and activation in the tcgen05 GEMM's epilogue."""
     return _LinearGeluFn.apply(x, weight, bias)
+
+
+class _MLPFn(torch.autograd.Function):
+    """y = W2 gelu(W1 x + b1) + b2 with the GELU in the first GEMM's epilogue (forward) and its derivative in the
+    epilogue of the backward GEMM dY.W2 — no stand-alone activation kernel in either direction."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        h, pre = linear_act(x, w1, b1, "gelu", save_pre=True)
+        y = torch.nn.functional.linear(h, w2, b2)
+        ctx.save_for_backward(x, w1, w2, pre, h)
+        ctx.params = ((w1, b1), (w2, b2))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .layers import linear_backward
+        x, w1, w2, pre, h = ctx.saved_tensors
+        p1, p2 = ctx.params
+        dy = dy.contiguous()
+        _, dw2, db2 = linear_backward(p2, h, w2, dy, needs_dx=False)
+        # dH = dY . W2 needs W2 as a K-major [N = d_hidden, K = d_model] operand: one 4.7 MB transpose per layer
+        du, _ = linear_act(dy, w2.t().contiguous(), None, "dgelu", aux=pre)
+        dx, dw1, db1 = linear_backward(p1, x, w1, du, ctx.needs_input_grad[0])
+        return dx, dw1, db1, dw2, db2
+
+
+def mlp_gelu(x, w1, b1, w2, b2):
+    """Transformer MLP ``linear(gelu(linear(x)))`` with both activation passes fused into tcgen05 GEMM epilogues."""
+    return _MLPFn.apply(x, w1, b1, w2, b2)

@@ -52,3 +52,38 @@ def test_linear_gelu_autograd_matches_torch(dev):
     for got, want in ((x.grad, xr.grad), (w.grad, wr.grad), (b.grad, br.grad)):
         err = (got.float() - want).abs().max() / want.abs().max()
         assert err < 3e-2, err
+
+
+@pytest.mark.skipif(os.environ.get("ADAPCC_EXPERIMENTAL", "0") != "1", reason="aux epilogue modes: first GPU run pending")
+def test_aux_epilogues_and_fused_mlp(dev):
+    from adapcc_b200.ops.gemm import linear_act, mlp_gelu
+
+    torch.manual_seed(5)
+    m, n, k = 384, 1024, 256
+    x = torch.randn(m, k, device=dev).bfloat16()
+    w = (torch.randn(n, k, device=dev) / k ** 0.5).bfloat16()
+    b = torch.randn(n, device=dev).bfloat16()
+    aux = torch.randn(m, n, device=dev).bfloat16()
+    acc = x.float() @ w.float().t()
+    got, _ = linear_act(x, w, b, "residual", aux=aux)
+    want = (acc + b.float()).bfloat16().float() + aux.float()
+    assert torch.allclose(got.float(), want, atol=4e-2, rtol=2e-2)
+    got, _ = linear_act(x, w, None, "dgelu", aux=aux)
+    a = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(a, approximate="tanh").sum().backward()
+    assert torch.allclose(got.float(), acc * a.grad, atol=4e-2, rtol=3e-2)
+    # whole MLP, both directions
+    d, hid = 256, 1024
+    xs = torch.randn(4, 96, d, device=dev).bfloat16().requires_grad_(True)
+    w1 = (torch.randn(hid, d, device=dev) / 16).bfloat16().requires_grad_(True)
+    b1 = torch.randn(hid, device=dev).bfloat16().requires_grad_(True)
+    w2 = (torch.randn(d, hid, device=dev) / 32).bfloat16().requires_grad_(True)
+    b2 = torch.randn(d, device=dev).bfloat16().requires_grad_(True)
+    dy = torch.randn(4, 96, d, device=dev).bfloat16()
+    mlp_gelu(xs, w1, b1, w2, b2).backward(dy)
+    ref = [t.detach().float().requires_grad_(True) for t in (xs, w1, b1, w2, b2)]
+    F = torch.nn.functional
+    F.linear(F.gelu(F.linear(ref[0], ref[1], ref[2]), approximate="tanh"), ref[3], ref[4]).backward(dy.float())
+    for got, want in zip((xs, w1, b1, w2, b2), ref):
+        err = (got.grad.float() - want.grad).abs().max() / want.grad.abs().max()
+        assert err < 3e-2, err

@@ -11,4 +11,5 @@ run() { n=$1; shift; env "$@" timeout 150 python bench.py --steps 20 --warmup 5 
 run default X=1
 run tc_mlp_v0 ADAPCC_TCGEN05_MLP=1
 [ "$VARIANTS" = "0,1" ] && run tc_mlp_v1 ADAPCC_TCGEN05_MLP=1 ADAPCC_TCGEN05_VARIANT=1
+grep -q "test_aux_epilogues_and_fused_mlp PASSED\|passed" gpurun_out/p1_tcgen05_v1.log && run tc_mlp_fwd_bwd ADAPCC_TCGEN05_MLP=2
 timeout 120 python tools/torch_profile_step.py --out gpurun_out/p1_torch_profile.md > gpurun_out/p1_torch_profile.log 2>&1; head -30 gpurun_out/p1_torch_profile.md
