@@ -114,29 +114,53 @@ def strategy_time(strategy: Strategy, lm: LinkModel, total_bytes: float, chunk_b
                for t in strategy.trees)
 
 
+# Constants of the direct-algorithm model, calibrated on the committed 8xB200 sweep
+# (profiles/allreduce_sweep_8xB200_final.json; tests/test_synth.py checks the model against that file):
+LAUNCH_US = 5.2            # fixed cost of one collective kernel (launch, first touch, last-block bookkeeping)
+BARRIER_ALPHAS = 1.5       # one per-CTA flag barrier = a peer store + a local poll ~ 1.5 link latencies
+STAGE_PASS_US = 3.3        # latency of one staging pass (stage-in or stage-out) over the window
+STAGE_GBS = 1640.0         # payload rate of a staging pass that is NOT overlapped with the link phase
+STAGE_PIPELINED_GBS = 4200.0   # ... of the pipelined staged two-shot (stager CTAs overlap the link CTAs)
+PIPELINE_MIN_BYTES = 32 << 20
+TWO_SHOT_LINK_EFF = 0.9    # pull + push share the NVLink ports: 625 of the profiled 700 GB/s
+NVLS_LINK_EFF = 0.77       # multimem.ld_reduce + multimem.st: 540 GB/s per GPU at 1 GiB
+
+
 def direct_times(lm: LinkModel, nbytes: float, ranks: Optional[Sequence[int]] = None,
-                 nvls: bool = True, nvls_bw_gbs: Optional[float] = None) -> Dict[str, float]:
-    """Closed-form estimates for the switch-topology algorithms (seconds)."""
+                 nvls: bool = True, nvls_bw_gbs: Optional[float] = None, zero_copy: bool = False) -> Dict[str, float]:
+    """Estimates (seconds) for the switch-topology algorithms on a message of ``nbytes`` wire bytes.
+
+    ``zero_copy``: the tensor lives in the symmetric heap, so the two-shot / NVLS kernels skip both staging passes
+    (a one-shot is always staged: peers read the window while the result is produced)."""
     rs = list(range(lm.world)) if ranks is None else list(ranks)
     n = max(2, len(rs))
     a = lm.mean_alpha(rs)
-    beta = 1.0 / (lm.min_bw(rs) * GB)
+    bw = lm.min_bw(rs) * GB
+    fixed = LAUNCH_US * 1e-6 + 2 * BARRIER_ALPHAS * a
+
+    def stage(passes: int, gbs: float = STAGE_GBS) -> float:
+        return passes * (STAGE_PASS_US * 1e-6 + nbytes / (gbs * GB))
+
+    two_shot_stage = 0.0 if zero_copy else stage(
+        2, STAGE_PIPELINED_GBS if nbytes >= PIPELINE_MIN_BYTES else STAGE_GBS)
     out = {
-        # one barrier + every rank pulls (n-1) windows + exit barrier
-        "one_shot": 3 * a + (n - 1) * nbytes * beta,
-        # barrier, pull slice from n-1 peers, push to n-1 peers, barrier
-        "two_shot": 4 * a + 2 * (n - 1) / n * nbytes * beta,
+        # stage-in, barrier, every rank pulls the other n-1 windows and writes the result directly, barrier
+        "one_shot": fixed + stage(1) + (n - 1) * nbytes / bw,
+        # [stage-in] barrier, pull my slice from n-1 peers, push it to n-1 peers, barrier [stage-out]
+        "two_shot": fixed + two_shot_stage + 2 * (n - 1) / n * nbytes / (TWO_SHOT_LINK_EFF * bw),
     }
     if nvls:
-        mb = 1.0 / ((nvls_bw_gbs or lm.min_bw(rs)) * GB)
+        mb = (nvls_bw_gbs * GB) if nvls_bw_gbs else NVLS_LINK_EFF * bw
         # the switch reduces on the way in (S/n per rank) and replicates on the way out (S)
-        out["nvls"] = 4 * a + (1.0 + 1.0 / n) * nbytes * mb
+        out["nvls"] = fixed + (0.0 if zero_copy else stage(2)) + (1.0 + 1.0 / n) * nbytes / mb
     return out
 
 
 def pick_algorithm(lm: LinkModel, nbytes: float, ranks=None, nvls: bool = True,
-                   strategy: Optional[Strategy] = None, chunk_bytes: float = 1 << 20) -> str:
-    t = direct_times(lm, nbytes, ranks, nvls)
+                   strategy: Optional[Strategy] = None, chunk_bytes: float = 1 << 20, zero_copy: bool = False) -> str:
+    t = direct_times(lm, nbytes, ranks, nvls, zero_copy=zero_copy)
+    if zero_copy:
+        t.pop("one_shot", None)             # in place a one-shot would race with the peers' reads
     if strategy is not None:
         t["tree"] = strategy_time(strategy, lm, nbytes, chunk_bytes)
     return min(t, key=t.get)
