@@ -53,6 +53,11 @@ class LinkModel:
         return bool(v) and (max(v) - min(v)) <= tol * max(v)
 
 
+# One hop of the strategy-tree kernel costs more than a link latency: the parent polls the child's flag over NVLink
+# (a round trip), then pulls; measured 44 us for a one-chunk 6-hop all-reduce on 8xB200 -> ~3.5 alpha per hop.
+TREE_HOP_ALPHAS = 3.5
+
+
 def tree_time(tree: Tree, lm: LinkModel, slice_bytes: float, chunk_bytes: float, bcast: bool = True,
               ingress_share: Optional[Dict[int, float]] = None) -> float:
     """Pipelined completion time of one reduction(+broadcast) tree over its slice.
@@ -66,18 +71,20 @@ def tree_time(tree: Tree, lm: LinkModel, slice_bytes: float, chunk_bytes: float,
     n_chunks = max(1.0, slice_bytes / chunk)
     step_max = 0.0
 
-    def step(x: int) -> float:
+    def step(x: int, lat: float = 1.0) -> float:
         kids = tree.kids(x)
         if not kids:
             return 0.0
         share = (ingress_share or {}).get(x, 1.0)
-        return max(lm.alpha(c, x) for c in kids) + sum(chunk * lm.beta(c, x) for c in kids) * share
+        return lat * max(lm.alpha(c, x) for c in kids) + sum(chunk * lm.beta(c, x) for c in kids) * share
 
     def fill(x: int) -> float:
+        # the FIRST chunk pays the full flag round trip at every level; later chunks overlap it across the CTA lanes,
+        # so the steady-state step below keeps one link latency
         kids = tree.kids(x)
         if not kids:
             return 0.0
-        return step(x) + max(fill(c) for c in kids)
+        return step(x, TREE_HOP_ALPHAS) + max(fill(c) for c in kids)
 
     for x in tree.nodes:
         step_max = max(step_max, step(x))
@@ -88,7 +95,7 @@ def tree_time(tree: Tree, lm: LinkModel, slice_bytes: float, chunk_bytes: float,
             kids = tree.kids(x)
             if not kids:
                 return 0.0
-            return max(lm.alpha(x, c) + chunk * lm.beta(x, c) + bfill(c) for c in kids)
+            return max(TREE_HOP_ALPHAS * lm.alpha(x, c) + chunk * lm.beta(x, c) + bfill(c) for c in kids)
         egress = max((len(tree.kids(x)) for x in tree.nodes), default=1)
         bstep = max((lm.alpha(x, c) + chunk * lm.beta(x, c) * max(1, len(tree.kids(x)))
                      for x in tree.nodes for c in tree.kids(x)), default=0.0)
@@ -110,8 +117,9 @@ def strategy_time(strategy: Strategy, lm: LinkModel, total_bytes: float, chunk_b
             if t.kids(x):
                 load[x] = load.get(x, 0) + 1
     per = total_bytes / nt
-    return max(tree_time(t, lm, per, chunk_bytes, bcast, {x: float(k) for x, k in load.items()})
-               for t in strategy.trees)
+    # + one kernel launch; user tensors are staged through the window on the way in and out
+    return LAUNCH_US * 1e-6 + max(tree_time(t, lm, per, chunk_bytes, bcast, {x: float(k) for x, k in load.items()})
+                                  for t in strategy.trees)
 
 
 # Constants of the direct-algorithm model, calibrated on the committed 8xB200 sweep
