@@ -80,3 +80,50 @@ def test_single_buffer_is_caught_by_the_model():
         except (AssertionError, TimeoutError):
             bad += 1
     assert bad > 0, "the model failed to expose the single-buffer hazard"
+
+
+def _ll_kernel_reference(inputs, elems_per_word):
+    """Line / word / tail index arithmetic of allreduce_ll_kernel (csrc/kernels_ll.cuh) replayed on Python lists:
+    every rank's message is cut into 32-bit words of E elements, two words per 16-byte line; a trailing odd element
+    (E == 2) travels alone in a zero-padded word and is written back alone."""
+    world, n, E = len(inputs), len(inputs[0]), elems_per_word
+    nwords = (n + E - 1) // E
+    nlines = (nwords + 1) // 2
+    outs = [[None] * n for _ in range(world)]
+
+    def words_of(rank, line):
+        w = []
+        for k in range(2):
+            wi = 2 * line + k
+            if (wi + 1) * E <= n:
+                w.append(tuple(inputs[rank][wi * E:(wi + 1) * E]))
+            elif wi * E < n:
+                w.append((inputs[rank][wi * E],) + (0,) * (E - 1))
+            else:
+                w.append((0,) * E)
+        return w
+
+    for me in range(world):
+        for line in range(nlines):
+            acc = None
+            for p in range(world):                           # rank order, own contribution in place
+                w = words_of(p, line)
+                acc = w if acc is None else [tuple(a + b for a, b in zip(x, y)) for x, y in zip(acc, w)]
+            for k in range(2):
+                wi = 2 * line + k
+                if (wi + 1) * E <= n:
+                    outs[me][wi * E:(wi + 1) * E] = list(acc[k])
+                elif wi * E < n:
+                    outs[me][wi * E] = acc[k][0]
+    return outs
+
+
+@pytest.mark.parametrize("elems_per_word", [1, 2])
+def test_ll_line_and_tail_indexing_covers_every_element_once(elems_per_word):
+    rng = random.Random(elems_per_word)
+    for n in list(range(1, 20)) + [255, 256, 257, 4097]:
+        for world in (2, 3, 8):
+            inputs = [[rng.randint(-50, 50) for _ in range(n)] for _ in range(world)]
+            want = [sum(col) for col in zip(*inputs)]
+            for out in _ll_kernel_reference(inputs, elems_per_word):
+                assert out == want, (n, world)
