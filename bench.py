@@ -124,7 +124,8 @@ def reference_arm(a):
            "transformers.AdamW + PersonaChat download")
     if os.path.isdir(ref) and os.listdir(ref):
         why = "baseline/_ref present but the reference has no runnable GPT-2 entry point offline: " + why
-    print(json.dumps({"impl": "reference", "unavailable": why}))
+    if int(os.environ.get("RANK", "0") or 0) == 0:          # one line per job, also under torchrun
+        print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
     return 0
 
 
