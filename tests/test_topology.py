@@ -42,3 +42,29 @@ def test_logical_graph_from_detect_xml(tmp_path):
     out = tmp_path / "lg.xml"
     xmlio.dump_file(g, out)
     assert topo.logical_graph_ranks(out) == {"a": [0, 1, 2, 3], "b": [4, 5, 6, 7]}
+
+
+def test_dispatcher_local_copy_dry_run_and_remote_commands(tmp_path, monkeypatch):
+    """File plane: local / shared-filesystem hosts are plain copies, remote hosts get one scp command per file set
+    (reference: /root/reference/dispatcher.py:7-54, which shells out to scp even for the local host)."""
+    from adapcc_b200.dispatcher import Dispatcher
+
+    src = tmp_path / "src"
+    dst = tmp_path / "dst"
+    src.mkdir()
+    for r in range(3):
+        (src / f"topo_detect_{r}.xml").write_text(f"<cpu id='{r}'/>")
+    monkeypatch.setenv("ADAPCC_SHARED_FS", "0")
+    d = Dispatcher(["127.0.0.1", "127.0.0.1", "10.9.8.7"], scp="scp", dry_run=True)
+    d.dispatch_detected_topo(str(src / "topo_detect*"), str(dst))
+    assert sorted(p.name for p in dst.iterdir()) == [f"topo_detect_{r}.xml" for r in range(3)]   # local copy happened
+    remote = [ln for ln in d.log if ln.startswith("scp ")]
+    assert len(remote) == 1 and remote[0].endswith(f"10.9.8.7:{dst}") and remote[0].count("topo_detect_") == 3
+    # shared filesystem: nothing is ever shelled out, whatever the address
+    monkeypatch.setenv("ADAPCC_SHARED_FS", "1")
+    d2 = Dispatcher(["10.9.8.7", "10.9.8.8"], dry_run=False)
+    d2.dispatch_ip_table(str(src / "topo_detect_0.xml"), str(tmp_path / "dst2"))
+    assert (tmp_path / "dst2" / "topo_detect_0.xml").exists()
+    assert not any(ln.startswith("scp ") for ln in d2.log)
+    d2.renew_ip_table(["127.0.0.1"])
+    assert list(d2.ip_dict) == ["127.0.0.1"]
