@@ -58,6 +58,10 @@ class MetricsSink:
 
 
 def busbw_gbs(nbytes: int, seconds: float, world: int, prim: str = "allreduce") -> float:
-    """nccl-tests definition (/root/reference/nccl-perf/benchmark/PERFORMANCE.md:33-142)."""
-    factor = 2 * (world - 1) / world if prim == "allreduce" else 1.0
+    """Bus bandwidth with the nccl-tests correction factors (/root/reference/nccl-perf/benchmark/PERFORMANCE.md:33-142):
+    all-reduce 2(n-1)/n, all-gather / reduce-scatter / all-to-all (n-1)/n of the TOTAL buffer size, reduce and
+    broadcast 1."""
+    n = max(1, world)
+    factor = {"allreduce": 2 * (n - 1) / n, "allgather": (n - 1) / n, "reducescatter": (n - 1) / n,
+              "alltoall": (n - 1) / n}.get(prim, 1.0)
     return nbytes / max(seconds, 1e-12) * factor / 1e9

@@ -141,3 +141,25 @@ def test_gns_and_checkpoint_helpers(tmp_path):
     st2 = State(m2, torch.optim.SGD(m2.parameters(), lr=0.1))
     assert st2.load(tmp_path / "ck.pt") and st2.epoch == 3 and st2.step == 17
     assert torch.equal(m.weight, m2.weight)
+
+
+def test_meters_and_metrics_sink(tmp_path, capsys):
+    import json
+
+    from adapcc_b200.utils.meters import AverageMeter, MetricsSink, ProgressMeter, busbw_gbs
+
+    m = AverageMeter("step", ":.2f")
+    for v in (1.0, 3.0):
+        m.update(v)
+    assert m.avg == 2.0 and str(m) == "step 3.00 (2.00)"
+    line = ProgressMeter(100, [m], prefix="it ").display(7)
+    assert "[  7/100]" in line and "step 3.00" in capsys.readouterr().out
+    sink = MetricsSink(str(tmp_path / "m" / "metrics.jsonl"), rank=3)
+    sink.emit("allreduce", bytes=1 << 20, seconds=1e-3)
+    rec = json.loads((tmp_path / "m" / "metrics.jsonl").read_text().strip())
+    assert rec["rank"] == 3 and rec["event"] == "allreduce" and rec["bytes"] == 1 << 20
+    MetricsSink(None).emit("noop")                              # disabled sink: silently ignored
+    # nccl-tests factors: 8 ranks, 1 GB in 1 ms
+    assert abs(busbw_gbs(10 ** 9, 1e-3, 8) - 1750.0) < 1e-6
+    assert abs(busbw_gbs(10 ** 9, 1e-3, 8, "alltoall") - 875.0) < 1e-6
+    assert abs(busbw_gbs(10 ** 9, 1e-3, 8, "boardcast") - 1000.0) < 1e-6
