@@ -5,6 +5,8 @@ import socket
 import sys
 import tempfile
 
+import pytest
+
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -163,3 +165,28 @@ def test_meters_and_metrics_sink(tmp_path, capsys):
     assert abs(busbw_gbs(10 ** 9, 1e-3, 8) - 1750.0) < 1e-6
     assert abs(busbw_gbs(10 ** 9, 1e-3, 8, "alltoall") - 875.0) < 1e-6
     assert abs(busbw_gbs(10 ** 9, 1e-3, 8, "boardcast") - 1000.0) < 1e-6
+
+
+def test_elastic_example_checkpoints_and_resumes_on_cpu(tmp_path):
+    """examples/elastic_imagenet.py (the reference's torchelastic workload) end to end on 2 gloo ranks: train one epoch,
+    write the checkpoint, restart with a larger epoch budget and resume after the saved epoch."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pytest.importorskip("torchvision")
+
+    def run(epochs, port):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+               "127.0.0.1", "--master-port", str(port), os.path.join(root, "examples", "elastic_imagenet.py"),
+               "--backend", "gloo", "--epochs", str(epochs), "--steps_per_epoch", "1", "--batch", "2",
+               "--checkpoint", str(tmp_path / "ckpt.pt")]
+        r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, PYTHONPATH=root))
+        assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+        return r.stdout
+
+    out = run(1, 29671)
+    assert "resuming from epoch 0" in out and (tmp_path / "ckpt.pt").exists()
+    out = run(2, 29672)
+    assert "resuming from epoch 1" in out and "Epoch: [1]" in out and "Epoch: [0]" not in out
