@@ -11,6 +11,8 @@ rank set, needed for BASELINE config 1: strategy/4.xml at world_size=2) and of i
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence
 
@@ -134,6 +136,8 @@ class Strategy:
         return "\n".join(out) + "\n"
 
     def save(self, path, compact: bool = False) -> None:
+        parent = os.path.dirname(os.path.abspath(path))
+        os.makedirs(parent, exist_ok=True)            # e.g. ./strategy/ when training starts outside the repo root
         with open(path, "w") as f:
             f.write(self.to_xml(compact))
 

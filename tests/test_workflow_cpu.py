@@ -190,3 +190,19 @@ def test_elastic_example_checkpoints_and_resumes_on_cpu(tmp_path):
     assert "resuming from epoch 0" in out and (tmp_path / "ckpt.pt").exists()
     out = run(2, 29672)
     assert "resuming from epoch 1" in out and "Epoch: [1]" in out and "Epoch: [0]" not in out
+
+
+def test_train_ddp_template_full_workflow_from_an_empty_directory(tmp_path):
+    """The reference's template script (train_ddp.py) under torchrun on 2 gloo ranks with entry_point 6, started in an
+    empty working directory: detect -> profile -> synthesise must create ./topology and ./strategy themselves."""
+    import subprocess
+
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29673", os.path.join(ROOT, "train_ddp.py"), "--backend", "gloo", "--model", "mlp",
+           "--batch", "8", "--steps", "3", "--entry_point", "6"]
+    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300, env=dict(os.environ, PYTHONPATH=ROOT))
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert "step 2" in r.stdout
+    assert (tmp_path / "strategy" / "strategy.xml").exists()
+    for f in ("ip_table.txt", "logical_graph.xml", "topo_profile_0", "topo_profile_1", "tunables.json"):
+        assert (tmp_path / "topology" / f).exists(), f
