@@ -206,3 +206,18 @@ def test_train_ddp_template_full_workflow_from_an_empty_directory(tmp_path):
     assert (tmp_path / "strategy" / "strategy.xml").exists()
     for f in ("ip_table.txt", "logical_graph.xml", "topo_profile_0", "topo_profile_1", "tunables.json"):
         assert (tmp_path / "topology" / f).exists(), f
+
+
+def test_wait_time_measurement_script_on_cpu(tmp_path):
+    """adapcc_b200/bench/wait_time.py (the reference's units-test/wait-time measurement) on 2 gloo ranks: writes the
+    per-step first-bucket gap CSV and prints the summary."""
+    import subprocess
+
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29674", "-m", "adapcc_b200.bench.wait_time", "--backend", "gloo", "--steps", "5",
+           "--heter_alpha", "1.5"]
+    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300, env=dict(os.environ, PYTHONPATH=ROOT))
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert "mean" in r.stdout and "median" in r.stdout
+    rows = (tmp_path / "wait_time.csv").read_text().strip().splitlines()
+    assert len(rows) >= 3
