@@ -221,3 +221,26 @@ def test_wait_time_measurement_script_on_cpu(tmp_path):
     assert "mean" in r.stdout and "median" in r.stdout
     rows = (tmp_path / "wait_time.csv").read_text().strip().splitlines()
     assert len(rows) >= 3
+
+
+def test_net_probe_bandwidth_and_latency_on_loopback():
+    """adapcc_b200/bench/net_probe.py (the reference's iperf / ping cloud traces, cloud/band_profile.py) against its own
+    server on loopback."""
+    import threading
+
+    from adapcc_b200.bench import net_probe
+
+    with socket.socket() as s:                                 # a free port
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    threading.Thread(target=net_probe.serve, args=(port,), daemon=True).start()
+    for _ in range(50):
+        try:
+            socket.create_connection(("127.0.0.1", port), timeout=0.2).close()
+            break
+        except OSError:
+            import time
+            time.sleep(0.05)
+    assert net_probe.bandwidth("127.0.0.1", port, duration=0.2) > 0.1          # Gb/s
+    lat = net_probe.latency("127.0.0.1", port, n=20)
+    assert 0 < lat < 50                                                         # ms
