@@ -10,6 +10,8 @@ reader accepts that dialect. The native runtime has an equivalent C++ reader
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass, field
 from typing import Dict, Iterator, List, Optional
 
@@ -185,5 +187,6 @@ def dumps(node: Node, indent: int = 4, header: bool = True) -> str:
 
 
 def dump_file(node: Node, path, **kw) -> None:
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     with open(path, "w") as f:
         f.write(dumps(node, **kw))
