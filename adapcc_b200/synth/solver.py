@@ -4,8 +4,9 @@ The reference builds a Gurobi model over root choice ``r_mg``, per-flow routing 
 size ``c_m``, aggregation control ``a_mj`` and link load ``N_mij`` — but it multiplies variables,
 never calls ``model.optimize()`` and never writes XML (/root/reference/gurobi/solver.py:11-211;
 SURVEY Appendix C.11). gurobipy is not installable here, so this is a linear reformulation that an
-open solver (HiGHS through ``scipy.optimize.milp``) solves in well under a second for 8 ranks and
-that really emits the strategy:
+open solver (HiGHS through ``scipy.optimize.milp``) handles — an incumbent within ~1 s for 8 ranks (the
+optimality proof of the highly symmetric switch case does not finish, so the solve is time-boxed) — and that
+really emits the strategy:
 
   variables   x[m,i,j] in {0,1}   rank i's parent in tree m is j      (reduce edge i -> j)
               r[m,g]   in {0,1}   g is the root of tree m
@@ -39,8 +40,9 @@ class SolverError(RuntimeError):
 
 
 class Solver:
-    def __init__(self, time_limit_s: float = 5.0, mip_rel_gap: float = 0.02):
+    def __init__(self, time_limit_s: float = 5.0, mip_rel_gap: float = 0.02, first_limit_s: float = 1.5):
         self.time_limit_s = time_limit_s
+        self.first_limit_s = first_limit_s
         self.mip_rel_gap = mip_rel_gap
         self.last_status: Optional[str] = None
         self.last_objective: Optional[float] = None
@@ -94,6 +96,11 @@ class Solver:
         cap = math.ceil(M / n)
         for g in range(n):           # spread the roots
             add({Rv(m, g): 1.0 for m in range(M)}, 0.0, float(cap))
+        if lm.is_uniform() and len({lm.bw_gbs[R[a]][R[b]] > 0 for a in range(n) for b in range(n) if a != b}) == 1:
+            # symmetry breaking on a switch (all links alike): which rank roots which tree is arbitrary, so pin
+            # tree m's root to rank m mod n instead of letting branch-and-bound explore the n!/(n-M)! relabelings
+            for m in range(M):
+                add({Rv(m, m % n): 1.0}, 1.0, 1.0)
         scale = 1e6                  # work in microseconds for conditioning
         for j in range(n):
             cin = {X(m, i, j): -s_m * lm.beta(R[i], R[j]) * scale for m in range(M) for i in range(n)
@@ -130,9 +137,15 @@ class Solver:
         ub = np.full(nv, np.inf)
         ub[off_x:off_d] = 1.0
         ub[off_d:off_D] = float(n - 1)
-        res = milp(c=cost, constraints=LinearConstraint(A.tocsr(), lo, hi), integrality=integrality,
-                   bounds=Bounds(lb, ub),
-                   options={"time_limit": self.time_limit_s, "mip_rel_gap": self.mip_rel_gap, "disp": False})
+        # The incumbent usually appears within a second and then only the (symmetric) optimality proof runs until the
+        # limit, so the first attempt is short; the long one only happens when nothing feasible was found yet.
+        res = None
+        for limit in (min(self.time_limit_s, self.first_limit_s), self.time_limit_s):
+            res = milp(c=cost, constraints=LinearConstraint(A.tocsr(), lo, hi), integrality=integrality,
+                       bounds=Bounds(lb, ub),
+                       options={"time_limit": limit, "mip_rel_gap": self.mip_rel_gap, "disp": False})
+            if res.x is not None or limit >= self.time_limit_s:
+                break
         self.last_status = str(res.message)
         if res.x is None:
             raise SolverError(f"MILP found no solution: {res.message}")
