@@ -14,6 +14,18 @@ from ..runtime.rendezvous import unique_name
 
 
 def main():
+    import argparse
+
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--native", action="store_true",
+                    help="run the stand-alone native binary adapcc_b200/_C/check_p2p instead (one process, all GPUs)")
+    a, rest = ap.parse_known_args()
+    if a.native:
+        import subprocess
+
+        from ..build import OUT_DIR, build
+        build()
+        raise SystemExit(subprocess.call([str(OUT_DIR / "check_p2p"), *rest]))
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
