@@ -83,6 +83,8 @@ bool parse_element(Cursor& c, XmlNode* out, int depth) {
         val = c.s.substr(vb, c.i - vb);
       }
     }
+    for (const auto& kv : out->attrs)
+      if (kv.first == key) { set_error("xml: attribute '%s' given twice on <%s>", key.c_str(), out->name.c_str()); return false; }
     out->attrs.emplace_back(key, val);
   }
   // children until the matching close tag
@@ -167,6 +169,10 @@ bool Strategy::load(const std::string& xml_text, int world) {
     StrategyTree t;
     if (!add_subtree(r, -1, &t)) return false;
     if (world > 0) t = contract(t, [world](int x) { return x < world; });
+    // The Python front end rejects trees that do not span every rank (Strategy.validate); a C caller of the
+    // reference ABI gets at least a warning: a rank outside a tree neither contributes to nor receives its slice.
+    if (world > 0 && t.root >= 0 && (int)t.nodes.size() != world)
+      ADAPCC_LOG(1, "strategy: tree %d covers %d of %d ranks", (int)trees.size(), (int)t.nodes.size(), world);
     if (t.root >= 0) trees.push_back(std::move(t));
     if ((int)trees.size() > kMaxTrees) { set_error("strategy: more than %d trees", kMaxTrees); return false; }
   }

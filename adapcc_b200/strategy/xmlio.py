@@ -135,6 +135,8 @@ def _parse_element(c: _Cursor, depth: int = 0) -> Node:
                 while not c.eof() and not c.s[c.i].isspace() and c.s[c.i] != ">" and not c.starts("/>"):
                     c.i += 1
                 val = c.s[vb:c.i]
+        if key in node.attrs:
+            raise XmlError(f"attribute '{key}' given twice on <{node.tag}>")
         node.attrs[key] = val
     while True:
         c.skip_misc()

@@ -138,3 +138,65 @@ def test_generated_strategies_are_spanning():
             s = make_strategy(world, 4, shape)
             s.validate(world)
             assert len({t.root for t in s.trees}) == len(s.trees)
+
+
+def test_python_and_native_parsers_agree_under_fuzzing():
+    """Differential fuzz of the two lenient strategy readers (strategy/xmlio.py and csrc/schedule.cpp): well-formed
+    dialect variants, truncations, deletions, duplicated chunks and garbage. Whenever both accept, the relay-control
+    rows must be identical; the native reader must never accept something whose result differs, and never crash."""
+    import random
+
+    from adapcc_b200.runtime.native import NativeError, native_relay_control
+    from adapcc_b200.strategy import Strategy, make_strategy
+    from adapcc_b200.strategy.relay import relay_control
+
+    rng = random.Random(11)
+
+    def mangle(xml):
+        c = rng.random()
+        if c < 0.25:
+            return xml.replace('" ip=', '"ip=').replace('" id=', '"id=')        # the reference's missing-space dialect
+        if c < 0.4:
+            return xml.replace(">", ">\n\t ").replace(" id=", "   id=")
+        if c < 0.55:
+            return xml[: rng.randrange(1, len(xml))]
+        if c < 0.7:
+            x = list(xml)
+            for _ in range(rng.randint(1, 5)):
+                del x[rng.randrange(len(x))]
+            return "".join(x)
+        if c < 0.8:
+            i = rng.randrange(len(xml))
+            j = min(len(xml), i + rng.randint(1, 40))
+            return xml[:j] + xml[i:j] + xml[j:]
+        if c < 0.9:
+            i = rng.randrange(len(xml))
+            return xml[:i] + "".join(rng.choice("<>/\"'= \n&;!-") for _ in range(rng.randint(1, 8))) + xml[i:]
+        return xml
+
+    agree = 0
+    for _ in range(400):
+        world = rng.choice([2, 3, 4, 8, 16])
+        deg = rng.choice([1, 2, 4])
+        xml = mangle(make_strategy(world, deg, rng.choice(["chain", "binary", "star"])).to_xml(compact=rng.random() < 0.5))
+        active = sorted(rng.sample(range(world), rng.randint(1, world)))
+        rank, tree = rng.randrange(world), rng.randrange(deg)
+        py = nat = None
+        try:
+            st = Strategy.from_xml(xml, world)
+            st.validate(world)
+            if tree < len(st.trees):
+                rc = relay_control(st.trees[tree], rank, active)
+                py = (bool(rc.has_recv), bool(rc.has_local), bool(rc.has_kernel), bool(rc.has_send),
+                      sorted(rc.active_recvs), len(st.trees))
+        except Exception:                                                     # noqa: BLE001  any rejection counts
+            py = None
+        try:
+            r = native_relay_control(xml, world, tree, rank, active)
+            nat = (r["has_recv"], r["has_local"], r["has_kernel"], r["has_send"], sorted(r["active_recvs"]), r["n_trees"])
+        except NativeError:
+            nat = None
+        if py is not None:
+            assert nat == py, (py, nat, xml[:300])
+            agree += 1
+    assert agree > 150
