@@ -4,6 +4,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -42,3 +44,37 @@ def test_shipped_strategies_parse_and_validate():
         assert s.trees
         world = len(s.ranks())
         s.validate(world)
+
+
+def test_sass_of_the_built_library_contains_the_hardware_paths():
+    """The evidence the design rests on, checked on the build box (cuobjdump needs no GPU): in-switch reductions
+    (LDGMC = multimem.ld_reduce), multicast stores, 128-bit peer accesses, system-scope release/acquire flags, and the
+    tensor-core path of the GEMM (UTCHMMA = tcgen05.mma, UTMALDG = TMA load, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit)."""
+    import re
+    import shutil
+    import subprocess
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    from adapcc_b200.build import build
+
+    lib = build()
+    sass = subprocess.run(["cuobjdump", "-sass", str(lib)], capture_output=True, text=True, timeout=600).stdout
+    assert "sm_100a" in sass
+    blocks = dict(zip(re.findall(r"Function : (\S+)", sass), re.split(r"\n\s*Function : \S+\n", sass)[1:]))
+
+    def ops_of(substr):
+        text = "\n".join(b for n, b in blocks.items() if substr in n)
+        assert text, f"no kernel matching {substr}"
+        return text
+
+    direct = ops_of("allreduce_direct_kernel")
+    for m in ("LDGMC", "STG.E.128.STRONG.SYS", "LDG.E.NA.128", "MEMBAR.ALL.SYS", "CCTL.IVALL"):
+        assert m in direct, m
+    tree = ops_of("tree_collective_kernel")
+    assert "LDG.E.64.STRONG.SYS" in tree and "STG.E.64.STRONG.SYS" in tree          # 64-bit chunk tokens
+    gemm = ops_of("gemm_bias_act_tcgen05")
+    for m in ("UTCHMMA", "UTMALDG.2D", "LDTM.x32", "UTCBAR", "SYNCS.PHASECHK"):
+        assert m in gemm, m
+    assert "STG.E.128.STRONG.SYS" in ops_of("zero_adamw_bcast_kernel")              # parameters leave through multimem.st
+    assert "LD.E.128.STRONG.SYS" in ops_of("allreduce_ll_kernel") or "LDG.E.128.STRONG.SYS" in ops_of("allreduce_ll_kernel")
