@@ -27,7 +27,7 @@ class AdapCC:
     profile_freq = None
 
     @classmethod
-    def init(cls, args, local_rank, world_rank, world_size):
+    def init(cls, args, local_rank, world_rank, world_size, _native=None):
         """Create the communicator and run the workflow stages ``args.entry_point`` asks for: 6 = DETECT
         (topology -> logical graph) then PROFILE (link microbench -> synthesised strategy XML), 7 = PROFILE only,
         -1 = keep ``args.strategy_file``. Collective over all ranks (reference: /root/reference/adapcc.py:16-42)."""
@@ -44,6 +44,7 @@ class AdapCC:
             except ImportError:
                 dylib = None
         cls.communicator = CudaCommu(args, dylib, local_rank, world_rank, world_size)
+        cls.communicator.adopt_native(_native)         # reconstruct_topology: keep the symmetric buffers alive
         cls.local_rank, cls.world_rank, cls.world_size = local_rank, world_rank, world_size
         cls.profile_freq = getattr(args, "profile_freq", None)
 
@@ -97,8 +98,11 @@ class AdapCC:
     def reconstruct_topology(cls, args, prim):
         """Re-run init (re-profile / re-synthesise per ``args.entry_point``) and rebuild the context for ``prim``; call
         it every ``profile_freq`` steps from the training loop (reference: /root/reference/adapcc.py:64-68)."""
-        cls.clear(prim)
-        cls.init(args, cls.local_rank, cls.world_rank, cls.world_size)
+        old = cls.communicator
+        old.exit_threads(prim)
+        native = old.clear(keep_native=True)           # DDP buckets / flat gradients may live in its heap
+        cls.init(args, cls.local_rank, cls.world_rank, cls.world_size, _native=native)
+        old._successor = cls.communicator              # hooks registered on the old object follow
         cls.setup(prim)
 
     @classmethod

@@ -284,9 +284,11 @@ class CudaCommu:
     # ==========================================================================================
     # workflow
     # ==========================================================================================
-    def clear(self):
+    def clear(self, keep_native: bool = False):
         """stop the controller and the grpc server (collective: a slower rank may still be
-        negotiating its last step, so nobody tears the coordinator down before everyone arrived)"""
+        negotiating its last step, so nobody tears the coordinator down before everyone arrived).
+        ``keep_native``: hand the native context (symmetric buffers, heap — DDP buckets may live in it) back to
+        the caller instead of destroying it; ``AdapCC.reconstruct_topology`` passes it to the next communicator."""
         if self.native is not None:
             import torch
 
@@ -301,10 +303,37 @@ class CudaCommu:
         if self.server is not None:
             self.server.stop(1)
             self.server = None
+        kept = None
         if self.native is not None:
             self._barrier()
-            self.native.close()
+            if keep_native:
+                kept = self.native
+            else:
+                self.native.close()
             self.native = None
+        self._cleared = True
+        return kept
+
+    def adopt_native(self, native) -> None:
+        """Reuse a live native context from a previous communicator (same world / device / buffer sizes): the
+        strategy and the tunables of THIS communicator are (re)applied when its primitive is set up."""
+        if native is None:
+            return
+        ok = (native.world == (self.world_size if self.single_server else len(self.node_ranks))
+              and native.staging_bytes >= self.staging_bytes and native.heap_bytes >= self.heap_bytes)
+        if not ok:                       # different shape: build a fresh one lazily, release the old one now
+            native.close()
+            return
+        self.native = native
+        self.native.set_tunable("relay_mode", self.relay_mode)
+        self._apply_tunables()
+
+    def _live(self):
+        """The communicator that replaced this one (``reconstruct_topology``), following the chain."""
+        c = self
+        while getattr(c, "_cleared", False) and getattr(c, "_successor", None) is not None:
+            c = c._successor
+        return c
 
     def update_relay(self, step):
         """called once per iteration before forward: heartbeat + (for relays) data-plane duty"""
@@ -680,6 +709,13 @@ class CudaCommu:
         (/root/reference/commu.py:385-435), backward keeps running."""
         import torch
 
+        if getattr(self, "_cleared", False):
+            # DDP keeps the bound method it was given at register_comm_hook time; after reconstruct_topology that is
+            # a cleared communicator -> hand the bucket to the live one (the reference re-creates the communicator
+            # the same way, /root/reference/adapcc.py:64-68, and leaves the hook dangling)
+            live = self._live()
+            if live is not self:
+                return live.cuda_allreduce_hook(state, bucket)
         if self.local_hook_num == 0 and self.relay_control:
             t0 = time.time()
             try:

@@ -71,6 +71,21 @@ def _worker(rank, world, port, coord_port, tmp, q):
         dist.all_gather(w, model.weight.detach())
         ok &= all(torch.allclose(w[0], x, atol=1e-6) for x in w)        # replicas stayed in sync
         ok &= len(comm.stats["hook_rpc_s"]) == 3
+        # the training-loop pattern of the reference's ViT script: reconstruct_topology in the middle of training; DDP
+        # still holds the hook of the communicator that is now cleared -> it must forward to the live one
+        stale = comm
+        AdapCC.reconstruct_topology(args, ALLREDUCE)
+        live = AdapCC.communicator
+        ok &= live is not stale and stale._live() is live
+        for step in range(2):
+            live.update_relay(step)
+            loss = ddp(torch.randn(8, 16)).pow(2).mean()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+        dist.all_gather(w, model.weight.detach())
+        ok &= all(torch.allclose(w[0], x, atol=1e-6) for x in w)
+        ok &= len(live.stats["hook_rpc_s"]) == 2 and len(stale.stats["hook_rpc_s"]) == 3
         AdapCC.clear(ALLREDUCE)
         q.put((rank, ok))
     finally:
