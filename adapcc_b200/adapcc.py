@@ -115,3 +115,66 @@ class AdapCC:
         """Tear down the context for ``prim`` and the control plane (collective; reference: /root/reference/adapcc.py:74-76)."""
         cls.communicator.exit_threads(prim)
         cls.communicator.clear()
+
+
+def _main():
+    """Primitive benchmark template — the ``__main__`` block of /root/reference/adapcc.py:81-117 (same flags, same
+    ``ones(16) * i`` all-reduce with 8-byte chunks, printed per rank), under torchrun instead of mpirun and with
+    ``--backend gloo`` for boxes without a GPU.
+
+        torchrun --nproc-per-node 8 -m adapcc_b200.adapcc --entry_point -1 --strategy_file strategy/8.xml
+    """
+    import argparse
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    parser = argparse.ArgumentParser(description="AdapCC primitive benchmark template")
+    parser.add_argument("--port", type=str, default="5000")
+    parser.add_argument("--strategy_file", type=str, default="./strategy/strategy.xml")
+    parser.add_argument("--logical_graph", type=str, default="./topology/logical_graph.xml")
+    parser.add_argument("--entry_point", type=int, default=-1)
+    parser.add_argument("--parallel_degree", type=int, default=4)
+    parser.add_argument("--profile_freq", type=int, default=500)
+    parser.add_argument("--backend", type=str, default="nccl", choices=["nccl", "gloo"])
+    args = parser.parse_args()
+
+    env = os.environ
+    local = int(env.get("LOCAL_RANK", env.get("OMPI_COMM_WORLD_LOCAL_RANK", 0)))
+    world = int(env.get("WORLD_SIZE", env.get("OMPI_COMM_WORLD_SIZE", 1)))
+    rank = int(env.get("RANK", env.get("OMPI_COMM_WORLD_RANK", 0)))
+    cuda = args.backend == "nccl" and torch.cuda.is_available()
+    if not cuda:
+        args.backend = "gloo"
+    env.setdefault("MASTER_ADDR", "127.0.0.1")
+    env.setdefault("MASTER_PORT", "29400")
+    if cuda:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    AdapCC.init(args, local, rank, world)
+    for prim, name in ((ALLREDUCE, "allreduce"), (REDUCE, "reduce"), (BOARDCAST, "boardcast")):
+        AdapCC.setup(prim)
+        for i in range(1, 3):
+            tensor = torch.ones(16, dtype=torch.float32) * i
+            if cuda:
+                tensor = tensor.to(local)
+            size, chunk_bytes, active = int(tensor.numel()), 8, list(range(world))
+            if prim == ALLREDUCE:
+                out = AdapCC.communicator.all_reduce(tensor, size, chunk_bytes, active)
+            elif prim == REDUCE:
+                out = AdapCC.communicator.reduce(tensor, size, chunk_bytes, active)
+            else:
+                out = AdapCC.communicator.boardcast(tensor, size, chunk_bytes)
+            if cuda:
+                AdapCC.communicator.synchronize()
+            print("rank %d %s:" % (rank, name), out.cpu().numpy().tolist(), flush=True)
+        AdapCC.communicator.exit_threads(prim)
+    AdapCC.communicator.clear()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    _main()

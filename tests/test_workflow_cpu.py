@@ -259,3 +259,20 @@ def test_net_probe_bandwidth_and_latency_on_loopback():
     assert net_probe.bandwidth("127.0.0.1", port, duration=0.2) > 0.1          # Gb/s
     lat = net_probe.latency("127.0.0.1", port, n=20)
     assert 0 < lat < 50                                                         # ms
+
+
+def test_primitive_benchmark_main_on_cpu(tmp_path):
+    """``python -m adapcc_b200.adapcc`` — the reference's benchmark ``__main__`` (adapcc.py:81-117): ones(16) * i through
+    all_reduce / reduce / boardcast on 2 gloo ranks."""
+    import subprocess
+
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29675", "-m", "adapcc_b200.adapcc", "--backend", "gloo"]
+    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300, env=dict(os.environ, PYTHONPATH=ROOT))
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("rank ")]
+    assert len(lines) == 12
+    assert "rank 0 allreduce: " + str([2.0] * 16) in lines and "rank 1 allreduce: " + str([4.0] * 16) in lines
+    # reduce: slice t of the sum lands on tree t's root only (reference semantics); broadcast: the roots' data everywhere
+    assert "rank 0 reduce: " + str([2.0] * 8 + [1.0] * 8) in lines and "rank 1 reduce: " + str([1.0] * 8 + [2.0] * 8) in lines
+    assert "rank 1 boardcast: " + str([1.0] * 16) in lines
