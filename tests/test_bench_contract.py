@@ -78,3 +78,14 @@ def test_sass_of_the_built_library_contains_the_hardware_paths():
         assert m in gemm, m
     assert "STG.E.128.STRONG.SYS" in ops_of("zero_adamw_bcast_kernel")              # parameters leave through multimem.st
     assert "LD.E.128.STRONG.SYS" in ops_of("allreduce_ll_kernel") or "LDG.E.128.STRONG.SYS" in ops_of("allreduce_ll_kernel")
+
+
+def test_drop_in_import_shims():
+    """``from adapcc import *`` (how the reference's train_ddp.py imports the library) and ``python launcher.py``."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = "import sys; sys.path.insert(0, %r); from adapcc import *; print(AdapCC.__name__, ALLREDUCE, REDUCE, BOARDCAST, DETECT, PROFILE)" % root
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.split() == ["AdapCC", "0", "1", "2", "6", "7"], out.stderr[-500:]
+    out = subprocess.run([sys.executable, os.path.join(root, "launcher.py"), "--num-process", "2", "--ips", "127.0.0.1:2",
+                          "--exec-file", "train_ddp.py", "--dry-run"], capture_output=True, text=True, timeout=120, cwd=root)
+    assert out.returncode == 0 and "torch.distributed.run" in out.stdout, out.stderr[-500:]
