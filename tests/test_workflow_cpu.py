@@ -276,3 +276,21 @@ def test_primitive_benchmark_main_on_cpu(tmp_path):
     # reduce: slice t of the sum lands on tree t's root only (reference semantics); broadcast: the roots' data everywhere
     assert "rank 0 reduce: " + str([2.0] * 8 + [1.0] * 8) in lines and "rank 1 reduce: " + str([1.0] * 8 + [2.0] * 8) in lines
     assert "rank 1 boardcast: " + str([1.0] * 16) in lines
+
+
+def test_training_survives_a_dead_worker_on_cpu(tmp_path):
+    """Fault tolerance end to end (reference README: "continued communication without being blocked by the straggler /
+    faulty"): 3 gloo ranks train through the DDP hook, rank 2 dies at step 2, ranks 0 and 1 finish all six steps with the
+    active set shrunk to [0, 1]."""
+    import subprocess
+
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr",
+           "127.0.0.1", "--master-port", "29676", os.path.join(ROOT, "tests", "cpu_fault_worker.py"), str(tmp_path),
+           str(_free_port())]
+    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300, env=dict(os.environ, PYTHONPATH=ROOT))
+    out = r.stdout + r.stderr
+    assert "[rank 2] dying at step 2" in out
+    for rank in (0, 1):
+        assert f"[rank {rank}] finished" in out, out[-3000:]
+        assert f"[rank {rank}] step 5 active [0, 1]" in out, out[-3000:]
+    assert "[rank 0] step 1 active [0, 1, 2]" in out
