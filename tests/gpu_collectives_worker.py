@@ -233,6 +233,34 @@ def main():
         "chain2": "<trees>" + "".join(chain_xml(o) for o in orders[:2]) + "</trees>",
         "binary": "<trees>" + "".join(bin_xml(o) for o in orders) + "</trees>",
     }
+    if os.environ.get("ADAPCC_EXPERIMENTAL", "0") == "1":
+        # random spanning trees (arbitrary fan-out and depth), the shapes the CPU property test covers
+        import random as _random
+
+        _rng = _random.Random(99)
+
+        def random_tree_xml():
+            order = list(range(world))
+            _rng.shuffle(order)
+            kids = {order[0]: []}
+            for r in order[1:]:
+                kids.setdefault(_rng.choice(list(kids)), []).append(r)
+                kids.setdefault(r, [])
+
+            def rec(a, tag):
+                return f"<{tag} id='{a}' ip='h'>" + "".join(rec(c, "gpu") for c in kids[a]) + f"</{tag}>"
+            return rec(order[0], "root")
+
+        for k in range(6):
+            xml = "<trees>" + "".join(random_tree_xml() for _ in range(1 + k % 3)) + "</trees>"
+            comm.load_strategy(xml)
+            for n, chunk in [(4097, 256), ((1 << 20) + 3, 1 << 16)]:
+                seed += 1
+                x = gen(rank, n, torch.float32, seed).to(dev)
+                comm.tree_collective(ALLREDUCE, x, op="sum", chunk_bytes=chunk)
+                comm.check()
+                check(f"tree[random{k}] allreduce n={n}", x, ref_reduce(world, n, torch.float32, seed, "sum", all_ranks),
+                      torch.float32, None, world * 2)
     for sname, xml in strategies.items():
         ntrees = comm.load_strategy(xml)
         for dtype, wire in [(torch.float32, None), (torch.float32, "bfloat16"), (torch.bfloat16, None)]:
