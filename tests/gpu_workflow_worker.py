@@ -84,6 +84,23 @@ def main():
     ok &= bool((t == world).all())
     if rank == 0:
         print(f"[workflow] reconstruct_topology: {(time.time() - t0) * 1e3:.0f} ms", flush=True)
+    # training continues with the SAME DDP object: its hook is bound to the cleared communicator (forwards to the live
+    # one) and its gradient buckets live in the symmetric heap of the native context that survived the reconstruct
+    for step in range(6, 9):
+        comm.update_relay(step)
+        loss = ddp(torch.randn(64, 512, device=dev)).pow(2).mean()
+        opt.zero_grad(set_to_none=False)
+        loss.backward()
+        opt.step()
+        torch.cuda.synchronize()
+    comm.synchronize()
+    if straggler < 0:                      # with relay steps the late rank's replica legitimately differs (BSP relays)
+        w0 = model[0].weight.detach().clone()
+        dist.broadcast(w0, src=0)
+        ok &= bool(torch.allclose(w0, model[0].weight.detach(), atol=1e-5))
+    ok &= len(comm.stats["hook_rpc_s"]) >= 1
+    if rank == 0:
+        print(f"[workflow] DDP across reconstruct: hook forwarded, {len(comm.stats['hook_rpc_s'])} negotiated steps", flush=True)
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     AdapCC.clear(ALLREDUCE)
