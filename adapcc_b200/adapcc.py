@@ -126,6 +126,7 @@ def _main():
     """
     import argparse
     import os
+    import sys
 
     import torch
     import torch.distributed as dist
@@ -170,7 +171,8 @@ def _main():
                 out = AdapCC.communicator.boardcast(tensor, size, chunk_bytes)
             if cuda:
                 AdapCC.communicator.synchronize()
-            print("rank %d %s:" % (rank, name), out.cpu().numpy().tolist(), flush=True)
+            sys.stdout.write("rank %d %s: %s\n" % (rank, name, out.cpu().numpy().tolist()))   # one write: ranks share a pipe
+            sys.stdout.flush()
         AdapCC.communicator.exit_threads(prim)
     AdapCC.communicator.clear()
     dist.destroy_process_group()

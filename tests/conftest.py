@@ -74,3 +74,12 @@ def strategy4_xml():
 @pytest.fixture
 def strategy_test_xml():
     return STRATEGY_TEST
+
+
+def free_port() -> int:
+    """A TCP port that is free right now (rendezvous ports of the multi-process CPU tests)."""
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]

@@ -8,6 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+from conftest import free_port
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -73,7 +75,8 @@ def test_public_api_handles_unusual_inputs_world3():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     tmp = tempfile.mkdtemp()
-    procs = [ctx.Process(target=_fuzz_worker, args=(r, world, 29731, tmp, q)) for r in range(world)]
+    port = free_port()
+    procs = [ctx.Process(target=_fuzz_worker, args=(r, world, port, tmp, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=180) for _ in procs]

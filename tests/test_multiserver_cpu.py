@@ -10,6 +10,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+from conftest import free_port
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -61,7 +63,8 @@ def test_two_server_workflow_on_cpu(entry):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     tmp = tempfile.mkdtemp()
-    procs = [ctx.Process(target=_ms_worker, args=(r, world, 29741 + entry, tmp, entry, q)) for r in range(world)]
+    port = free_port()
+    procs = [ctx.Process(target=_ms_worker, args=(r, world, port, tmp, entry, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=240) for _ in procs]

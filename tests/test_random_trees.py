@@ -11,6 +11,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+from conftest import free_port
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -83,7 +85,8 @@ def test_cpu_executor_on_random_trees_world6():
     world = 6
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_prop_worker, args=(r, world, 29751, q)) for r in range(world)]
+    port = free_port()
+    procs = [ctx.Process(target=_prop_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in procs]

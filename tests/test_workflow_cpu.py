@@ -14,10 +14,21 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_ports(n):
+    """n DISTINCT free TCP ports (all sockets are held open until every port is known: two back-to-back single probes
+    can return the same port)."""
+    socks = [socket.socket() for _ in range(n)]
+    try:
+        for s in socks:
+            s.bind(("127.0.0.1", 0))
+        return [s.getsockname()[1] for s in socks]
+    finally:
+        for s in socks:
+            s.close()
+
+
 def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
+    return _free_ports(1)[0]
 
 
 def _worker(rank, world, port, coord_port, tmp, q):
@@ -97,7 +108,7 @@ def test_detect_profile_synth_setup_reconstruct_hook_cpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     with tempfile.TemporaryDirectory() as tmp:
-        port, cport = _free_port(), _free_port()
+        port, cport = _free_ports(2)
         procs = [ctx.Process(target=_worker, args=(r, world, port, cport, tmp, q)) for r in range(world)]
         [p.start() for p in procs]
         [p.join(180) for p in procs]
@@ -191,19 +202,20 @@ def test_elastic_example_checkpoints_and_resumes_on_cpu(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pytest.importorskip("torchvision")
 
-    def run(epochs, port):
+    def run(epochs):
+        port, cport = _free_ports(2)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
                "127.0.0.1", "--master-port", str(port), os.path.join(root, "examples", "elastic_imagenet.py"),
                "--backend", "gloo", "--epochs", str(epochs), "--steps_per_epoch", "1", "--batch", "2",
                "--checkpoint", str(tmp_path / "ckpt.pt")]
         r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300,
-                           env=dict(os.environ, PYTHONPATH=root))
+                           env=dict(os.environ, PYTHONPATH=root, ADAPCC_COORD_PORT=str(cport)))
         assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
         return r.stdout
 
-    out = run(1, 29671)
+    out = run(1)
     assert "resuming from epoch 0" in out and (tmp_path / "ckpt.pt").exists()
-    out = run(2, 29672)
+    out = run(2)
     assert "resuming from epoch 1" in out and "Epoch: [1]" in out and "Epoch: [0]" not in out
 
 
@@ -212,10 +224,12 @@ def test_train_ddp_template_full_workflow_from_an_empty_directory(tmp_path):
     empty working directory: detect -> profile -> synthesise must create ./topology and ./strategy themselves."""
     import subprocess
 
+    mport, cport = _free_ports(2)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29673", os.path.join(ROOT, "train_ddp.py"), "--backend", "gloo", "--model", "mlp",
+           "127.0.0.1", "--master-port", str(mport), os.path.join(ROOT, "train_ddp.py"), "--backend", "gloo", "--model", "mlp",
            "--batch", "8", "--steps", "3", "--entry_point", "6"]
-    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300, env=dict(os.environ, PYTHONPATH=ROOT))
+    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, PYTHONPATH=ROOT, ADAPCC_COORD_PORT=str(cport)))
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "step 2" in r.stdout
     assert (tmp_path / "strategy" / "strategy.xml").exists()
@@ -228,10 +242,12 @@ def test_wait_time_measurement_script_on_cpu(tmp_path):
     per-step first-bucket gap CSV and prints the summary."""
     import subprocess
 
+    mport, cport = _free_ports(2)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29674", "-m", "adapcc_b200.bench.wait_time", "--backend", "gloo", "--steps", "5",
+           "127.0.0.1", "--master-port", str(mport), "-m", "adapcc_b200.bench.wait_time", "--backend", "gloo", "--steps", "5",
            "--heter_alpha", "1.5"]
-    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300, env=dict(os.environ, PYTHONPATH=ROOT))
+    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, PYTHONPATH=ROOT, ADAPCC_COORD_PORT=str(cport)))
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "mean" in r.stdout and "median" in r.stdout
     rows = (tmp_path / "wait_time.csv").read_text().strip().splitlines()
@@ -266,9 +282,11 @@ def test_primitive_benchmark_main_on_cpu(tmp_path):
     all_reduce / reduce / boardcast on 2 gloo ranks."""
     import subprocess
 
+    mport, cport = _free_ports(2)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29675", "-m", "adapcc_b200.adapcc", "--backend", "gloo"]
-    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300, env=dict(os.environ, PYTHONPATH=ROOT))
+           "127.0.0.1", "--master-port", str(mport), "-m", "adapcc_b200.adapcc", "--backend", "gloo"]
+    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, PYTHONPATH=ROOT, ADAPCC_COORD_PORT=str(cport)))
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("rank ")]
     assert len(lines) == 12
@@ -284,10 +302,12 @@ def test_training_survives_a_dead_worker_on_cpu(tmp_path):
     active set shrunk to [0, 1]."""
     import subprocess
 
+    mport, cport = _free_ports(2)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr",
-           "127.0.0.1", "--master-port", "29676", os.path.join(ROOT, "tests", "cpu_fault_worker.py"), str(tmp_path),
-           str(_free_port())]
-    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300, env=dict(os.environ, PYTHONPATH=ROOT))
+           "127.0.0.1", "--master-port", str(mport), os.path.join(ROOT, "tests", "cpu_fault_worker.py"), str(tmp_path),
+           str(cport)]
+    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, PYTHONPATH=ROOT, ADAPCC_COORD_PORT=str(cport)))
     out = r.stdout + r.stderr
     assert "[rank 2] dying at step 2" in out
     for rank in (0, 1):
