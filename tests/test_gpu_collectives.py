@@ -9,6 +9,8 @@ import sys
 import pytest
 import torch
 
+from conftest import free_port
+
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -20,7 +22,7 @@ def test_collectives_multi_gpu():
     world = 4 if n >= 4 else 2
     env = dict(os.environ, ADAPCC_TIMEOUT_MS="15000")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29517",
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
            os.path.join(ROOT, "tests", "gpu_collectives_worker.py"), "--quick"]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     tail = (r.stdout + r.stderr)[-4000:]
@@ -37,7 +39,7 @@ def test_zero1_engine_matches_data_parallel():
     world = 4 if n >= 4 else 2
     env = dict(os.environ, ADAPCC_TIMEOUT_MS="15000")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tests", "gpu_zero1_worker.py")]
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "tests", "gpu_zero1_worker.py")]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     tail = (r.stdout + r.stderr)[-4000:]
     assert r.returncode == 0, tail
