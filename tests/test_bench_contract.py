@@ -89,3 +89,28 @@ def test_drop_in_import_shims():
     out = subprocess.run([sys.executable, os.path.join(root, "launcher.py"), "--num-process", "2", "--ips", "127.0.0.1:2",
                           "--exec-file", "train_ddp.py", "--dry-run"], capture_output=True, text=True, timeout=120, cwd=root)
     assert out.returncode == 0 and "torch.distributed.run" in out.stdout, out.stderr[-500:]
+
+
+def test_launch_report_tool_on_a_sample_ncu_csv(tmp_path):
+    """tools/launch_report.py: ncu launch list (CSV with ==PROF== noise lines, mixed units) -> per-family table of the
+    last step, our kernels marked."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rows = ['==PROF== Connected to process 1', '"ID","Kernel Name","Metric Name","Metric Unit","Metric Value"']
+    k = 0
+    for step in range(2):
+        for name, unit, val in (("void adapcc::ln_fwd_kernel<3, true>(const __nv_bfloat16*)", "us", "12.5"),
+                                ("nvjet_tst_192x256_64x5_2x2_2cta_v_bz_NNT", "us", "30.0"),
+                                ("void at::native::vectorized_elementwise_kernel<4, F>(int)", "ns", "7,500"),
+                                ("void adapcc::adamw_kernel<__nv_bfloat16, __nv_bfloat16>(float*)", "ms", "0.5")):
+            rows.append(f'"{k}","{name}","gpu__time_duration.sum","{unit}","{val}"')
+            k += 1
+    src = tmp_path / "launches.csv"
+    src.write_text("\n".join(rows) + "\n")
+    out = tmp_path / "report.md"
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "launch_report.py"), str(src), "2", str(out), "sample"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-500:]
+    text = out.read_text()
+    assert "the last step (4 launches, 0.55 ms" in text
+    assert "**adapcc::adamw_kernel** (ours) | 1 | 0.500" in text and "**adapcc::ln_fwd_kernel** (ours) | 1 | 0.013" in text
+    assert "Our kernels: 93.2%" in text
