@@ -537,6 +537,171 @@ gemm_bias_act_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_
   if (warp == 1) tmem_free<kTmemCols>(tmem_base);
 }
 
+// =====================================================================================================
+// Variant 2 (CTA pair, cta_group::2; NOT yet run on a GPU — compiled and SASS-checked only):
+//   a cluster of two CTAs (two SMs of one TPC) owns a 256 x 256 output tile. CTA r stages ITS 128 rows of A and ITS
+//   128 rows of W per K-slab (32 KB per stage instead of 48 KB), the leader (cluster rank 0) issues
+//   tcgen05.mma.cta_group::2 with M = 256: the tensor cores of both SMs read both shared memories, CTA r's TMEM
+//   receives rows 128 r .. 128 r + 127 of the accumulator. Per output element the pair pulls half as many operand
+//   bytes through L2 as two independent 128 x 256 CTAs (arithmetic intensity 128 instead of 85 FLOP/B) — the
+//   reason the library GEMMs it competes with are 2-CTA kernels.
+//   Barriers: full[s] lives in the leader and counts the TMA bytes of BOTH CTAs (the peer's loads signal the
+//   leader's barrier: mbarrier address with the CTA bit cleared); empty[s] and acc_full exist in both CTAs and are
+//   signalled together by tcgen05.commit ... multicast::cluster with mask 0b11.
+// =====================================================================================================
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;        // clears the CTA-rank bit of a shared::cluster address -> CTA 0
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem) {   // one whole warp in EACH CTA, same dst offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_free_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// this CTA's slab; completion bytes are credited to the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, int c_inner, int c_outer,
+                                                 uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar & kPeerBitMask), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in BOTH CTAs once the issued MMAs have completed
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  const unsigned short mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+
+struct SmemPair {
+  static constexpr uint32_t kABytes = kBM * kBK * 2;             // this CTA's 128 rows of A
+  static constexpr uint32_t kBBytes = 128 * kBK * 2;             // this CTA's 128 rows of W
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;     // 32 KB
+  static constexpr int kStagesPair = 6;                          // 192 KB
+  static constexpr uint32_t kBarOffset = kStagesPair * kStageBytes;
+  static constexpr uint32_t kTotal = kBarOffset + (2 * kStagesPair + 1) * 8 + 16;
+  static constexpr uint32_t kDynamic = kTotal + 1024;
+};
+
+template <int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_bias_act_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                                  const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                  __nv_bfloat16* __restrict__ pre, int M, int N, int K, int tiles_n) {
+  constexpr int BN = 256;                                         // accumulator columns per CTA (full tile width)
+  constexpr int kS = SmemPair::kStagesPair;
+  extern __shared__ uint8_t smem_raw[];
+  // both CTAs must end up with IDENTICAL offsets (descriptors and barrier addresses are shared): the dynamic smem
+  // window starts at the same shared-space address in every CTA of a kernel, so the same rounding applies
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  using S = SmemPair;
+  const uint32_t bar0 = base + S::kBarOffset;
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (kS + s); };
+  const uint32_t acc_full = bar0 + 8u * (2 * kS);
+  const uint32_t tmem_slot = acc_full + 8u;
+  auto smem_a = [&](int s) { return base + (uint32_t)s * S::kStageBytes; };
+  auto smem_b = [&](int s) { return base + (uint32_t)s * S::kStageBytes + S::kABytes; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();                         // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int m_blk = pair / tiles_n, n_blk = pair % tiles_n;       // 256 x 256 tile of the pair
+  const int row0 = m_blk * 256 + (int)cta * 128;                  // this CTA's rows of A / of the output
+  const int wrow0 = n_blk * 256 + (int)cta * 128;                 // this CTA's rows of W (columns of the output tile)
+  const int num_kb = K / kBK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < kS; ++s) {
+      mbar_init(full(s), 1);                                      // only the leader's copy is ever used
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc_2cta<BN>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();                                             // the peer's barriers exist before anyone signals them
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs; bytes are counted on the leader's full[s]) =====
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kS;
+        const uint32_t ph = (uint32_t)(kb / kS) & 1u;
+        mbar_wait(empty(s), ph ^ 1u);                             // my own copy: commit arrives on both CTAs
+        if (cta == 0) mbar_expect_tx(full(s), 2 * S::kStageBytes);
+        tma_load_2d_2cta(smem_a(s), &map_a, kb * kBK, row0, full(s));
+        tma_load_2d_2cta(smem_b(s), &map_w, kb * kBK, wrow0, full(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && cta == 0) {
+      // ===== MMA issuer: leader only =====
+      constexpr uint32_t idesc = instr_desc_bf16(256, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kS;
+        const uint32_t ph = (uint32_t)(kb / kS) & 1u;
+        mbar_wait(full(s), ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          const uint64_t da = smem_desc_k_sw128(smem_a(s) + (uint32_t)k * kUmmaK * 2);
+          const uint64_t db = smem_desc_k_sw128(smem_b(s) + (uint32_t)k * kUmmaK * 2);
+          umma_bf16_2cta(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit_2cta(empty(s));
+      }
+      umma_commit_2cta(acc_full);
+    }
+  } else {
+    // ===== epilogue (both CTAs, each drains its own 128 accumulator rows) =====
+    const int q = warp & 3;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int row = row0 + q * 32 + lane;
+    const size_t row_off = (size_t)row * (size_t)N + (size_t)n_blk * BN;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), acc);
+      epilogue_chunk<ACT>(acc, bias ? bias + (size_t)n_blk * BN + c * 32 : nullptr, out + row_off + c * 32,
+                          pre ? pre + row_off + c * 32 : nullptr, row < M);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                                             // both CTAs are done with TMEM and with each other's smem
+  if (warp == 1) tmem_free_2cta<BN>(tmem_base);
+}
+
 // ---- host ----------------------------------------------------------------------------------------
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -612,6 +777,24 @@ static int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mw, const
   return 0;
 }
 
+template <int ACT>
+static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mw, const void* bias, void* out, void* pre, int M,
+                       int N, int K, cudaStream_t s) {
+  auto kern = gemm_bias_act_tcgen05_pair_kernel<ACT>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemPair::kDynamic));
+    configured = true;
+  }
+  const int tiles_n = N / 256, tiles_m = (M + 255) / 256;
+  kern<<<2 * tiles_n * tiles_m, kThreads, SmemPair::kDynamic, s>>>(ma, mw, (const __nv_bfloat16*)bias,
+                                                                   (__nv_bfloat16*)out, (__nv_bfloat16*)pre, M, N, K,
+                                                                   tiles_n);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 }  // namespace tc
 }  // namespace adapcc
 
@@ -622,8 +805,8 @@ extern "C" {
 // out = act(a[M,K] @ w[N,K]^T + bias); pre (optional) = the pre-activation. bf16 row-major, 16-byte aligned.
 // act 2: out = (a @ w^T) * gelu'(aux); act 3: out = a @ w^T + bias + aux — aux is passed in `pre` (an input then).
 // Constraints of this first version: K % 64 == 0, N % 128 == 0 (256-wide tiles when N % 256 == 0).
-// variant 0: one tile per CTA (validated on B200). variant 1: persistent CTAs, double-buffered TMEM accumulator
-// (compiled only so far).
+// variant 0: one tile per CTA (validated on B200). variant 1: persistent CTAs, double-buffered TMEM accumulator;
+// variant 2: CTA pairs (cta_group::2, 256 x 256 tile per pair) — both compiled only so far.
 int adapcc_gemm_bias_act_v(const void* a, const void* w, const void* bias, void* out, void* pre, int M, int N, int K,
                            int act, int variant, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
@@ -631,13 +814,19 @@ int adapcc_gemm_bias_act_v(const void* a, const void* w, const void* bias, void*
   if (act < 0 || act > 3) { set_error("gemm_tcgen05: act must be 0 (none), 1 (gelu_tanh), 2 (dgelu * aux) or 3 (+ aux)"); return -1; }
   if (act >= 2 && pre == nullptr) { set_error("gemm_tcgen05: act %d needs the aux tensor (passed as `pre`)", act); return -1; }
   if (act >= 2 && variant != 0) { set_error("gemm_tcgen05: act %d is only built for variant 0", act); return -1; }
-  if (variant != 0 && variant != 1) { set_error("gemm_tcgen05: variant must be 0 or 1"); return -1; }
+  if (variant < 0 || variant > 2) { set_error("gemm_tcgen05: variant must be 0, 1 or 2"); return -1; }
+  if (variant == 2 && (N % 256 != 0 || act > 1)) { set_error("gemm_tcgen05: variant 2 (CTA pairs) needs N %% 256 == 0 and act 0/1"); return -1; }
   if (((uintptr_t)a | (uintptr_t)w | (uintptr_t)out | (uintptr_t)pre | (uintptr_t)bias) & 15) { set_error("gemm_tcgen05: operands must be 16-byte aligned"); return -1; }
   const int bn = (N % 256 == 0) ? 256 : 128;
   CUtensorMap ma, mw;
   if (tc::make_map(&ma, a, M, K, tc::kBM)) return -1;
   if (tc::make_map(&mw, w, N, K, bn)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
+  if (variant == 2) {
+    CUtensorMap mw2;                                   // each CTA of a pair loads 128 rows of W per K-slab
+    if (tc::make_map(&mw2, w, N, K, 128)) return -1;
+    return act ? tc::launch_pair<1>(ma, mw2, bias, out, pre, M, N, K, s) : tc::launch_pair<0>(ma, mw2, bias, out, pre, M, N, K, s);
+  }
   if (variant == 1) {
     if (bn == 256) return act ? tc::launch_persistent<256, 1>(ma, mw, bias, out, pre, M, N, K, s) : tc::launch_persistent<256, 0>(ma, mw, bias, out, pre, M, N, K, s);
     return act ? tc::launch_persistent<128, 1>(ma, mw, bias, out, pre, M, N, K, s) : tc::launch_persistent<128, 0>(ma, mw, bias, out, pre, M, N, K, s);

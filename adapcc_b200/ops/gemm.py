@@ -35,8 +35,9 @@ def supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
 
 
 def default_variant() -> int:
-    """0: one output tile per CTA (validated on B200). 1: persistent CTAs with a double-buffered TMEM accumulator
-    (``ADAPCC_TCGEN05_VARIANT=1``; compiled and SASS-checked, first GPU run pending)."""
+    """0: one output tile per CTA (validated on B200). 1: persistent CTAs with a double-buffered TMEM accumulator.
+    2: CTA pairs (``tcgen05.mma.cta_group::2``, 256 x 256 tile per pair, half the operand traffic per output).
+    1 and 2 are compiled and SASS-checked, first GPU run pending (``ADAPCC_TCGEN05_VARIANT``)."""
     return int(os.environ.get("ADAPCC_TCGEN05_VARIANT", "0"))
 
 

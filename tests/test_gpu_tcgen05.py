@@ -7,9 +7,12 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-# variant 1 (persistent CTAs, double-buffered TMEM) has been compiled and SASS-checked but not run yet: a protocol
-# bug would trap the kernel and poison this process's CUDA context, so it only runs when asked for
-VARIANTS = [0, 1] if os.environ.get("ADAPCC_EXPERIMENTAL", "0") == "1" else [0]
+# variants 1 (persistent CTAs, double-buffered TMEM) and 2 (CTA pairs, cta_group::2) have been compiled and SASS-checked
+# but not run yet: a protocol bug would trap the kernel and poison this process's CUDA context, so they only run when
+# asked for, one process per variant: ADAPCC_EXPERIMENTAL=1 ADAPCC_TCGEN05_TEST_VARIANTS=1 (or 2, or 1,2)
+VARIANTS = [0]
+if os.environ.get("ADAPCC_EXPERIMENTAL", "0") == "1":
+    VARIANTS += [int(v) for v in os.environ.get("ADAPCC_TCGEN05_TEST_VARIANTS", "1,2").split(",") if v.strip()]
 
 
 @pytest.fixture(scope="module")
@@ -26,6 +29,8 @@ def dev():
 def test_gemm_bias_act_matches_fp32_reference(dev, m, n, k, act, variant):
     from adapcc_b200.ops.gemm import linear_act
 
+    if variant == 2 and n % 256 != 0:
+        pytest.skip("CTA-pair variant needs N % 256 == 0")
     torch.manual_seed(m + n + k)
     x = torch.randn(m, k, device=dev).bfloat16()
     w = (torch.randn(n, k, device=dev) / k ** 0.5).bfloat16()

@@ -156,3 +156,102 @@ def test_model_catches_a_wrong_parity(bug):
         except (AssertionError, TimeoutError):
             caught += 1
     assert caught == 10
+
+
+def simulate_pair(num_kb, seed, stages=6, bug=None, max_steps=200_000):
+    """Variant 2 (CTA pair): both CTAs produce, only the leader issues MMAs; the leader's full[s] counts the TMA bytes
+    of both CTAs, commits arrive on empty[s] / acc_full of BOTH CTAs at once (multicast)."""
+    rng = random.Random(seed)
+    full = [MBar(1) for _ in range(stages)]                       # leader's copy only
+    empty = [[MBar(1) for _ in range(stages)] for _ in range(2)]
+    acc_full = [MBar(1), MBar(1)]
+    smem = [[None] * stages for _ in range(2)]                    # [cta][stage] -> kb held
+    acc = []
+    tma_q, tc_q = deque(), deque()
+    done = []
+
+    def producer(cta):
+        for kb in range(num_kb):
+            s, ph = kb % stages, (kb // stages) & 1
+            while not empty[cta][s].done(ph ^ 1 if bug != "pair_parity" else ph):
+                yield
+            if cta == 0:
+                full[s].arrive(expect_tx=4)                       # A and W slabs of both CTAs
+            tma_q.append((cta, s, kb))
+            tma_q.append((cta, s, kb))
+            yield
+
+    def mma():
+        for kb in range(num_kb):
+            s, ph = kb % stages, (kb // stages) & 1
+            while not full[s].done(ph):
+                yield
+            tc_q.append(("mma", s, kb))
+            tc_q.append(("commit", [empty[0][s], empty[1][s]]))
+            yield
+        tc_q.append(("commit", acc_full))
+        yield
+
+    def epilogue(cta):
+        while not acc_full[cta].done(0):
+            yield
+        assert acc == list(range(num_kb)), acc
+        done.append(cta)
+        yield
+
+    def tma_engine():
+        while True:
+            if tma_q and rng.random() < 0.6:
+                i = rng.randrange(min(len(tma_q), 3))             # the two CTAs' loads complete in any order
+                cta, s, kb = tma_q[i]
+                del tma_q[i]
+                smem[cta][s] = kb
+                full[s].complete_tx(1)
+            yield
+
+    def tensor_core():
+        while True:
+            if tc_q and rng.random() < 0.6:
+                op = tc_q.popleft()
+                if op[0] == "commit":
+                    for b in op[1]:
+                        b.arrive()
+                else:
+                    _, s, kb = op
+                    assert smem[0][s] == kb and smem[1][s] == kb, (kb, smem[0][s], smem[1][s])
+                    acc.append(kb)
+            yield
+
+    roles = {"p0": producer(0), "p1": producer(1), "mma": mma(), "e0": epilogue(0), "e1": epilogue(1)}
+    engines = [tma_engine(), tensor_core()]
+    steps = 0
+    while roles:
+        steps += 1
+        if steps > max_steps:
+            raise TimeoutError(f"deadlock: {sorted(roles)}")
+        for e in engines:
+            next(e)
+        name = rng.choice(sorted(roles))
+        for _ in range(rng.randint(1, 5)):
+            try:
+                next(roles[name])
+            except StopIteration:
+                del roles[name]
+                break
+    assert sorted(done) == [0, 1]
+
+
+@pytest.mark.parametrize("num_kb", [1, 5, 6, 12, 48])
+def test_cta_pair_protocol_is_consistent(num_kb):
+    for seed in range(15):
+        simulate_pair(num_kb, seed)
+
+
+def test_cta_pair_model_catches_a_wrong_parity():
+    caught = 0
+    for seed in range(10):
+        try:
+            simulate_pair(24, seed, bug="pair_parity", max_steps=30_000)
+        except (AssertionError, TimeoutError):
+            caught += 1
+    assert caught == 10
