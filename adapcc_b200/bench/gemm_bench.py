@@ -39,7 +39,7 @@ def main() -> int:
     ap.add_argument("--n", type=int, default=3072)
     ap.add_argument("--k", type=int, default=768)
     ap.add_argument("--iters", type=int, default=50)
-    ap.add_argument("--variants", default="0,1")
+    ap.add_argument("--variants", default="0", help="comma list of tcgen05 kernel variants to time (0 validated; 1, 2 once they pass their tests)")
     ap.add_argument("--json", default="")
     a = ap.parse_args()
     from adapcc_b200.ops.gemm import linear_act
