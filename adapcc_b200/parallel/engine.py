@@ -293,6 +293,51 @@ class FlatDataParallel:
         self.steps_done += 1
         return self._static_loss
 
+    # -- checkpoint / resume -------------------------------------------------------------------------
+    def state_dict(self) -> Dict[str, object]:
+        """Everything needed to resume: fp32 master weights and AdamW moments PER PARAMETER NAME (so a checkpoint
+        survives a different bucket size, parameter order or world size), the step counter and the hyper-parameters.
+        In ``zero1`` mode the moments of slices owned by other ranks are stale on this rank: save from every rank or
+        all-gather first (the engine keeps full-size buffers, so loading a complete state is always possible)."""
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        per = {}
+        for p, off in zip(self.params, self._offsets):
+            n = p.numel()
+            per[names[id(p)]] = {"master": self.master[off:off + n].detach().cpu().clone().view(p.shape),
+                                 "exp_avg": self.exp_avg[off:off + n].detach().cpu().clone().view(p.shape),
+                                 "exp_avg_sq": self.exp_avg_sq[off:off + n].detach().cpu().clone().view(p.shape)}
+        return {"format": 1, "steps_done": int(self.steps_done), "step_t": int(self.step_t.item()),
+                "hyper": {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                          "max_norm": self.max_norm, "optimizer": self.optimizer}, "params": per}
+
+    def load_state_dict(self, sd: Dict[str, object], strict: bool = True) -> None:
+        """In place (buffer addresses — and therefore a captured CUDA graph — stay valid): fp32 state from the
+        checkpoint, bf16 parameters re-derived from the master weights."""
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        per = sd["params"]
+        missing = [names[id(p)] for p in self.params if names[id(p)] not in per]
+        if missing and strict:
+            raise KeyError(f"checkpoint lacks optimizer state for {missing[:5]}{'...' if len(missing) > 5 else ''}")
+        with torch.no_grad():
+            for p, off in zip(self.params, self._offsets):
+                e = per.get(names[id(p)])
+                if e is None:
+                    continue
+                n = p.numel()
+                if tuple(e["master"].shape) != tuple(p.shape):
+                    raise ValueError(f"{names[id(p)]}: checkpoint shape {tuple(e['master'].shape)} != {tuple(p.shape)}")
+                self.master[off:off + n].copy_(e["master"].reshape(-1))
+                self.exp_avg[off:off + n].copy_(e["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(e["exp_avg_sq"].reshape(-1))
+                self.flat_param[off:off + n].copy_(self.master[off:off + n])          # fp32 -> param dtype
+        self.steps_done = int(sd.get("steps_done", 0))
+        self.step_t.fill_(int(sd.get("step_t", self.steps_done)))
+        h = sd.get("hyper", {})
+        new_lr = h.get("lr", self.lr)
+        if self._graph is not None and new_lr != self.lr:
+            raise RuntimeError("the learning rate is baked into the captured graph: load the checkpoint before capture()")
+        self.lr = new_lr
+
     def close(self) -> None:
         for h in self._hooks:
             h.remove()

@@ -126,3 +126,35 @@ def test_moe_mlp_matches_a_per_token_reference_on_cpu():
     y = moe(x)
     kept = (y.abs().sum(-1) > 0).sum().item()
     assert kept <= 2 * moe.capacity(64) and kept < 64
+
+
+def test_flat_engine_state_dict_roundtrip_on_cpu():
+    """Checkpoint / resume of the flat engine: per-parameter-name fp32 state, restored in place into an engine with a
+    different bucket layout; bf16 parameters are re-derived from the master weights."""
+    from adapcc_b200.parallel.engine import FlatDataParallel
+
+    torch.manual_seed(0)
+    cfg = GPT2Config.tiny()
+    a = FlatDataParallel(GPT2DoubleHeads(cfg), None, world_size=1, lr=3e-4, bucket_mb=0.05)
+    a.master.normal_()                                   # pretend some training happened
+    a.exp_avg.uniform_(-1, 1)
+    a.exp_avg_sq.uniform_(0, 1)
+    a.steps_done = 17
+    a.step_t.fill_(17)
+    sd = a.state_dict()
+    assert sd["steps_done"] == 17 and set(sd["params"]) == {n for n, _ in a.model.named_parameters()}
+    torch.manual_seed(1)
+    b = FlatDataParallel(GPT2DoubleHeads(cfg), None, world_size=1, lr=1e-3, bucket_mb=1.0)
+    assert len(b.buckets) != len(a.buckets)
+    ptr = b.flat_param.data_ptr()
+    b.load_state_dict(sd)
+    assert b.flat_param.data_ptr() == ptr and b.steps_done == 17 and int(b.step_t.item()) == 17 and b.lr == 3e-4
+    for (na, pa), (nb, pb) in zip(a.model.named_parameters(), b.model.named_parameters()):
+        ea, eb = sd["params"][na], b.state_dict()["params"][nb]
+        assert torch.equal(ea["master"], eb["master"]) and torch.equal(ea["exp_avg_sq"], eb["exp_avg_sq"])
+        assert torch.equal(pb.detach().float(), ea["master"].to(pb.dtype).float())       # params follow the masters
+    bad = dict(sd, params={k: v for k, v in list(sd["params"].items())[1:]})
+    import pytest
+    with pytest.raises(KeyError):
+        b.load_state_dict(bad)
+    b.load_state_dict(bad, strict=False)
