@@ -45,6 +45,7 @@ def main():
     p.add_argument("--mc_coef", type=float, default=1.0)
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--tiny", action="store_true")
+    p.add_argument("--checkpoint", default="", help="flat engine: resume from this file if it exists, write it at the end")
     p.add_argument("--fuse_add_ln", action="store_true", help="residual adds fused into the following LayerNorm")
     p.add_argument("--lm_rows", default="all", choices=["all", "scored"],
                    help="scored: LM head only on rows with a label (same loss/gradients, ~1/8 of the rows)")
@@ -73,6 +74,10 @@ def main():
     if a.engine == "flat":
         eng = FlatDataParallel(model, comm.native if world > 1 else None, world_size=world, rank=rank, lr=a.lr,
                                max_norm=a.max_norm)
+        if a.checkpoint and os.path.exists(a.checkpoint):            # before capture: the lr is baked into the graph
+            eng.load_state_dict(torch.load(a.checkpoint, map_location="cpu", weights_only=False))
+            if rank == 0:
+                print("resumed from %s at step %d" % (a.checkpoint, eng.steps_done), flush=True)
         if a.graph:
             eng.capture(batches[0])
         step = (lambda b: eng.step_graph(b)) if a.graph else (lambda b: eng.step(b))
@@ -102,6 +107,9 @@ def main():
         if rank == 0:
             print("step %d loss %.4f computation time: %.3f" % (i, loss.item(), time.time() - t0), flush=True)
     comm.synchronize()
+    if a.checkpoint and a.engine == "flat" and rank == 0:            # replicas are identical: one writer
+        torch.save(eng.state_dict(), a.checkpoint + ".tmp")
+        os.replace(a.checkpoint + ".tmp", a.checkpoint)
     AdapCC.clear(ALLREDUCE)
     dist.destroy_process_group()
 
