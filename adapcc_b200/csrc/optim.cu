@@ -61,7 +61,8 @@ template <typename P, typename G>
 __global__ void __launch_bounds__(512)
 adamw_kernel(P* __restrict__ param, const G* __restrict__ grad, float* __restrict__ master, float* __restrict__ m,
              float* __restrict__ v, long long n, AdamArgs a, const float* __restrict__ sumsq,
-             const int* __restrict__ step_ptr) {
+             const int* __restrict__ step_ptr, const float* __restrict__ lr_ptr) {
+  if (lr_ptr != nullptr) a.lr = *lr_ptr;   // device-resident learning rate: schedules work under CUDA-graph replay
   if (step_ptr != nullptr) {   // device-resident step counter: keeps the launch CUDA-graph replayable
     const float t = (float)(*step_ptr);
     a.bias1 = 1.f - powf(a.beta1, t);
@@ -136,6 +137,11 @@ using namespace adapcc;
 
 extern "C" {
 
+int adapcc_fused_adamw_lr(void* param, const void* grad, float* master, float* m, float* v, long long n,
+                          int param_dtype, int grad_dtype, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, int step, float max_norm, float grad_scale, const float* sumsq,
+                          const int* step_ptr, const float* lr_ptr, void* stream);
+
 // out must be zeroed by the caller (cudaMemsetAsync on the same stream); accumulates.
 int adapcc_sumsq(const void* g, long long n, int dtype, float* out, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
@@ -156,6 +162,15 @@ int adapcc_fused_adamw(void* param, const void* grad, float* master, float* m, f
                        int param_dtype, int grad_dtype, float lr, float beta1, float beta2, float eps,
                        float weight_decay, int step, float max_norm, float grad_scale, const float* sumsq,
                        const int* step_ptr, void* stream) {
+  return adapcc_fused_adamw_lr(param, grad, master, m, v, n, param_dtype, grad_dtype, lr, beta1, beta2, eps, weight_decay,
+                               step, max_norm, grad_scale, sumsq, step_ptr, nullptr, stream);
+}
+
+// Same, with an optional device-resident learning rate (lr_ptr != NULL overrides `lr`).
+int adapcc_fused_adamw_lr(void* param, const void* grad, float* master, float* m, float* v, long long n,
+                          int param_dtype, int grad_dtype, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, int step, float max_norm, float grad_scale, const float* sumsq,
+                          const int* step_ptr, const float* lr_ptr, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (n <= 0) return 0;
   if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(master) |
@@ -171,13 +186,13 @@ int adapcc_fused_adamw(void* param, const void* grad, float* master, float* m, f
   int blocks = (int)std::min<long long>(1184, (n / 4 + 511) / 512);
   if (blocks < 1) blocks = 1;
   if (param_dtype == BF16 && grad_dtype == BF16)
-    adamw_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 512, 0, s>>>((__nv_bfloat16*)param, (const __nv_bfloat16*)grad, master, m, v, n, a, sumsq, step_ptr);
+    adamw_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 512, 0, s>>>((__nv_bfloat16*)param, (const __nv_bfloat16*)grad, master, m, v, n, a, sumsq, step_ptr, lr_ptr);
   else if (param_dtype == F32 && grad_dtype == F32)
-    adamw_kernel<float, float><<<blocks, 512, 0, s>>>((float*)param, (const float*)grad, master, m, v, n, a, sumsq, step_ptr);
+    adamw_kernel<float, float><<<blocks, 512, 0, s>>>((float*)param, (const float*)grad, master, m, v, n, a, sumsq, step_ptr, lr_ptr);
   else if (param_dtype == BF16 && grad_dtype == F32)
-    adamw_kernel<__nv_bfloat16, float><<<blocks, 512, 0, s>>>((__nv_bfloat16*)param, (const float*)grad, master, m, v, n, a, sumsq, step_ptr);
+    adamw_kernel<__nv_bfloat16, float><<<blocks, 512, 0, s>>>((__nv_bfloat16*)param, (const float*)grad, master, m, v, n, a, sumsq, step_ptr, lr_ptr);
   else if (param_dtype == F32 && grad_dtype == BF16)
-    adamw_kernel<float, __nv_bfloat16><<<blocks, 512, 0, s>>>((float*)param, (const __nv_bfloat16*)grad, master, m, v, n, a, sumsq, step_ptr);
+    adamw_kernel<float, __nv_bfloat16><<<blocks, 512, 0, s>>>((float*)param, (const __nv_bfloat16*)grad, master, m, v, n, a, sumsq, step_ptr, lr_ptr);
   else { set_error("adamw: unsupported dtypes %d/%d", param_dtype, grad_dtype); return -1; }
   CUDA_TRY(cudaGetLastError());
   count_launch();

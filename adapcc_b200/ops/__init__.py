@@ -24,6 +24,9 @@ def _lib():
         lib.adapcc_fused_adamw.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int,
                                            c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_float,
                                            c_void_p, c_void_p, c_void_p]
+        lib.adapcc_fused_adamw_lr.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int,
+                                              c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_float,
+                                              c_void_p, c_void_p, c_void_p, c_void_p]
         lib.adapcc_fused_sgd.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_float, c_float,
                                          c_void_p]
         lib.adapcc_incr_int.argtypes = [c_void_p, c_void_p]
@@ -57,15 +60,17 @@ def sumsq_(grad: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
 def fused_adamw_(param: torch.Tensor, grad: torch.Tensor, master: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *,
                  lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01, step: int = 1,
                  max_norm: float = 0.0, grad_scale: float = 1.0, sumsq: Optional[torch.Tensor] = None,
-                 step_tensor: Optional[torch.Tensor] = None) -> None:
+                 step_tensor: Optional[torch.Tensor] = None, lr_tensor: Optional[torch.Tensor] = None) -> None:
     """One launch: clip (coefficient derived on the device from ``sumsq``), AdamW on the fp32
     master/m/v, write-back of the (bf16 or fp32) parameters. ``step_tensor`` (int32 on device) makes
-    the bias correction replayable inside a CUDA graph."""
-    _ck(_lib().adapcc_fused_adamw(c_void_p(param.data_ptr()), c_void_p(grad.data_ptr()), c_void_p(master.data_ptr()),
-                                  c_void_p(m.data_ptr()), c_void_p(v.data_ptr()), param.numel(), _dt(param), _dt(grad),
-                                  lr, betas[0], betas[1], eps, weight_decay, int(step), max_norm, grad_scale,
-                                  c_void_p(sumsq.data_ptr() if sumsq is not None else None),
-                                  c_void_p(step_tensor.data_ptr() if step_tensor is not None else None), _stream()),
+    the bias correction replayable inside a CUDA graph; ``lr_tensor`` (fp32 on device) does the same for the learning
+    rate, so a schedule only has to update that scalar between replays."""
+    _ck(_lib().adapcc_fused_adamw_lr(c_void_p(param.data_ptr()), c_void_p(grad.data_ptr()), c_void_p(master.data_ptr()),
+                                     c_void_p(m.data_ptr()), c_void_p(v.data_ptr()), param.numel(), _dt(param), _dt(grad),
+                                     lr, betas[0], betas[1], eps, weight_decay, int(step), max_norm, grad_scale,
+                                     c_void_p(sumsq.data_ptr() if sumsq is not None else None),
+                                     c_void_p(step_tensor.data_ptr() if step_tensor is not None else None),
+                                     c_void_p(lr_tensor.data_ptr() if lr_tensor is not None else None), _stream()),
         "fused_adamw")
 
 

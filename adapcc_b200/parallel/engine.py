@@ -117,6 +117,7 @@ class FlatDataParallel:
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_t = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.lr_t = torch.full((1,), float(lr), dtype=torch.float32, device=dev)    # read by the optimizer kernel
         off = 0
         self._offsets: List[int] = []
         with torch.no_grad():
@@ -231,10 +232,16 @@ class FlatDataParallel:
                 sumsq = self.sumsq
             fused_adamw_(self.flat_param, self.flat_grad, self.master, self.exp_avg, self.exp_avg_sq, lr=self.lr,
                          betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, step=self.steps_done + 1,
-                         max_norm=self.max_norm or 0.0, sumsq=sumsq, step_tensor=self.step_t)
+                         max_norm=self.max_norm or 0.0, sumsq=sumsq, step_tensor=self.step_t, lr_tensor=self.lr_t)
         else:
             fused_sgd_(self.flat_param, self.flat_grad, self.master, lr=self.lr)
         return loss.detach()
+
+    def set_lr(self, lr: float) -> None:
+        """Change the learning rate (e.g. from a scheduler, once per step). The optimizer kernel reads it from a device
+        scalar, so this also takes effect in an already captured CUDA graph."""
+        self.lr = float(lr)
+        self.lr_t.fill_(self.lr)
 
     def _zero1_update(self) -> None:
         """Sharded optimizer step: norm of my slices -> 4-byte all-reduce -> AdamW on my slices with the parameter
@@ -333,10 +340,7 @@ class FlatDataParallel:
         self.steps_done = int(sd.get("steps_done", 0))
         self.step_t.fill_(int(sd.get("step_t", self.steps_done)))
         h = sd.get("hyper", {})
-        new_lr = h.get("lr", self.lr)
-        if self._graph is not None and new_lr != self.lr:
-            raise RuntimeError("the learning rate is baked into the captured graph: load the checkpoint before capture()")
-        self.lr = new_lr
+        self.set_lr(h.get("lr", self.lr))
 
     def close(self) -> None:
         for h in self._hooks:

@@ -45,6 +45,9 @@ def main():
     p.add_argument("--mc_coef", type=float, default=1.0)
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--tiny", action="store_true")
+    p.add_argument("--linear_decay", action="store_true",
+                   help="flat engine: lr decays linearly to 0 over --steps (the reference's PiecewiseLinear schedule, "
+                        "models/gpt2/train_gpt2_ddp.py); works under --graph, the kernel reads lr from a device scalar")
     p.add_argument("--checkpoint", default="", help="flat engine: resume from this file if it exists, write it at the end")
     p.add_argument("--fuse_add_ln", action="store_true", help="residual adds fused into the following LayerNorm")
     p.add_argument("--lm_rows", default="all", choices=["all", "scored"],
@@ -102,6 +105,8 @@ def main():
         if i and AdapCC.profile_freq and i % AdapCC.profile_freq == 0 and a.engine == "ddp":
             AdapCC.reconstruct_topology(a, ALLREDUCE)
         t0 = time.time()
+        if a.linear_decay and a.engine == "flat":
+            eng.set_lr(a.lr * max(0.0, 1.0 - i / max(1, a.steps)))
         loss = step(batches[i % len(batches)])
         torch.cuda.synchronize()
         if rank == 0:

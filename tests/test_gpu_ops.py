@@ -281,6 +281,39 @@ def test_gpt2_fused_residual_path_matches_unfused(dev):
     eng.close()
 
 
+def test_adamw_device_learning_rate_and_engine_set_lr(dev):
+    """lr read from a device scalar: overrides the launch argument, and set_lr() takes effect inside a captured graph."""
+    from adapcc_b200.models.gpt2 import GPT2Config, GPT2DoubleHeads, synthetic_batch
+    from adapcc_b200.ops import fused_adamw_
+    from adapcc_b200.parallel.engine import FlatDataParallel
+
+    torch.manual_seed(1)
+    n = 4099
+    g = torch.randn(n, device=dev)
+    outs = []
+    for lr_arg, lr_dev in ((3e-3, None), (123.0, 3e-3)):            # the tensor wins over a deliberately absurd argument
+        p = torch.ones(n, device=dev)
+        master, m, v = p.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        lr_t = None if lr_dev is None else torch.full((1,), lr_dev, device=dev)
+        fused_adamw_(p, g, master, m, v, lr=lr_arg, step=1, lr_tensor=lr_t)
+        outs.append(p.clone())
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], torch.ones(n, device=dev))
+    cfg = GPT2Config.tiny()
+    batch = synthetic_batch(2, 2, 32, cfg.vocab_size, device=dev)
+    torch.manual_seed(2)
+    eng = FlatDataParallel(GPT2DoubleHeads(cfg).to(dev), None, world_size=1, lr=2e-3)
+    eng.capture(batch, warmup=0)
+    eng.step_graph(batch)
+    before = eng.flat_param.clone()
+    eng.step_graph(batch)
+    assert not torch.equal(before, eng.flat_param)                  # training moves the weights ...
+    frozen = eng.flat_param.clone()
+    eng.set_lr(0.0)
+    eng.step_graph(batch)
+    assert torch.equal(frozen, eng.flat_param)                      # ... until the schedule says lr = 0, same graph
+    eng.close()
+
+
 def test_engine_direct_grads_match_accumulated(dev):
     """Fused ops writing parameter gradients straight into the flat buffer vs autograd accumulation."""
     from adapcc_b200.models.gpt2 import GPT2Config, GPT2DoubleHeads, synthetic_batch
