@@ -46,8 +46,9 @@ def main():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--tiny", action="store_true")
     p.add_argument("--linear_decay", action="store_true",
-                   help="flat engine: lr decays linearly to 0 over --steps (the reference's PiecewiseLinear schedule, "
-                        "models/gpt2/train_gpt2_ddp.py); works under --graph, the kernel reads lr from a device scalar")
+                   help="flat engine: lr decays linearly to 0 over --steps (the schedule of the conversational-AI script the "
+                        "reference's GPT-2 workload derives from; it imports ignite's PiecewiseLinear, "
+                        "train_gpt2_ddp.py:21). Works under --graph: the kernel reads lr from a device scalar")
     p.add_argument("--checkpoint", default="", help="flat engine: resume from this file if it exists, write it at the end")
     p.add_argument("--fuse_add_ln", action="store_true", help="residual adds fused into the following LayerNorm")
     p.add_argument("--lm_rows", default="all", choices=["all", "scored"],
