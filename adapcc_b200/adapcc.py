@@ -31,6 +31,11 @@ class AdapCC:
         """Create the communicator and run the workflow stages ``args.entry_point`` asks for: 6 = DETECT
         (topology -> logical graph) then PROFILE (link microbench -> synthesised strategy XML), 7 = PROFILE only,
         -1 = keep ``args.strategy_file``. Collective over all ranks (reference: /root/reference/adapcc.py:16-42)."""
+        prev = cls.communicator
+        if prev is not None and _native is None and not getattr(prev, "_cleared", False):
+            # init() on top of a live communicator (no clear() in between): tear the old one down first instead of
+            # leaking its coordinator server, controller thread and symmetric buffers
+            prev.clear()
         dylib = None
         if getattr(args, "backend", "nccl") != "gloo":
             try:
@@ -63,27 +68,33 @@ class AdapCC:
             print("no supported entry point for init.")
 
     @classmethod
+    def _comm(cls) -> CudaCommu:
+        if cls.communicator is None:
+            raise RuntimeError("AdapCC.init(args, local_rank, world_rank, world_size) has not been called")
+        return cls.communicator
+
+    @classmethod
     def setup(cls, prim):
         """Build the data-plane context for ``prim`` (ALLREDUCE / REDUCE / BOARDCAST / ALLTOALL): symmetric buffers,
         strategy tables, coordinator + controller when relay control is on (reference: /root/reference/adapcc.py:44-46)."""
-        cls.communicator.init_threads(prim)
+        cls._comm().init_threads(prim)
 
     @classmethod
     def allreduce(cls, tensor, size=None, chunk_bytes=None, active_gpus=None):
         """In-place all-reduce (sum) of the first ``size`` elements of ``tensor`` over ``active_gpus`` (default: all),
         asynchronous on the current stream; returns the tensor (reference: /root/reference/adapcc.py:48-50)."""
-        return cls.communicator.all_reduce(tensor, size, chunk_bytes, active_gpus)
+        return cls._comm().all_reduce(tensor, size, chunk_bytes, active_gpus)
 
     @classmethod
     def reduce(cls, tensor, size=None, chunk_bytes=None, active_gpus=None):
         """In-place reduce: every strategy tree's root ends up with the sum of its slice (direct algorithms: rank 0
         holds the whole result) — reference semantics, /root/reference/adapcc.py:52-54."""
-        return cls.communicator.reduce(tensor, size, chunk_bytes, active_gpus)
+        return cls._comm().reduce(tensor, size, chunk_bytes, active_gpus)
 
     @classmethod
     def boardcast(cls, tensor, size=None, chunk_bytes=None):
         """Broadcast (the reference's spelling): every rank receives the roots' data (reference: /root/reference/adapcc.py:56-58)."""
-        return cls.communicator.boardcast(tensor, size, chunk_bytes)
+        return cls._comm().boardcast(tensor, size, chunk_bytes)
 
     @classmethod
     def alltoall(cls, tensor, size=None, chunk_bytes=None):
@@ -92,7 +103,7 @@ class AdapCC:
         all-to-all of equal splits, carried by the expert-parallel dispatch kernels."""
         from .parallel.alltoall import all_to_all_single
 
-        return all_to_all_single(cls.communicator, tensor, size)
+        return all_to_all_single(cls._comm(), tensor, size)
 
     @classmethod
     def reconstruct_topology(cls, args, prim):
@@ -113,8 +124,8 @@ class AdapCC:
     @classmethod
     def clear(cls, prim):
         """Tear down the context for ``prim`` and the control plane (collective; reference: /root/reference/adapcc.py:74-76)."""
-        cls.communicator.exit_threads(prim)
-        cls.communicator.clear()
+        cls._comm().exit_threads(prim)
+        cls._comm().clear()
 
 
 def _main():

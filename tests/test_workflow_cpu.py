@@ -314,3 +314,19 @@ def test_training_survives_a_dead_worker_on_cpu(tmp_path):
         assert f"[rank {rank}] finished" in out, out[-3000:]
         assert f"[rank {rank}] step 5 active [0, 1]" in out, out[-3000:]
     assert "[rank 0] step 1 active [0, 1, 2]" in out
+
+
+def test_api_misuse_is_handled(tmp_path):
+    """Calls in the wrong order must end in a clear error or be harmless — never in a leaked server or a hang."""
+    import subprocess
+
+    mport, cport = _free_ports(2)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cpu_api_misuse_worker.py"), str(mport), str(cport)],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=180, env=dict(os.environ, PYTHONPATH=ROOT))
+    out = r.stdout
+    assert r.returncode == 0, (out + r.stderr)[-2000:]
+    assert "use before init -> RuntimeError AdapCC.init(" in out
+    assert "unknown prim -> NotImplementedError" in out
+    for case in ("allreduce before setup", "double init", "setup twice", "setup other prims", "reduce", "clear unknown prim",
+                 "clear", "clear twice", "use after clear"):
+        assert f"{case} -> ok" in out, out
