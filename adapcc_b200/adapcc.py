@@ -114,6 +114,10 @@ class AdapCC:
         native = old.clear(keep_native=True)           # DDP buckets / flat gradients may live in its heap
         cls.init(args, cls.local_rank, cls.world_rank, cls.world_size, _native=native)
         old._successor = cls.communicator              # hooks registered on the old object follow
+        # the DDP buckets did not change: keep what the hook learned about them at step 1 (sizes, relay scratch), or a
+        # relay of the new communicator would not know how many ops to mirror
+        cls.communicator.bucket_info = list(old.bucket_info)
+        cls.communicator.relay_buffer = list(old.relay_buffer)
         cls.setup(prim)
 
     @classmethod
