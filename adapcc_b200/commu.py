@@ -740,6 +740,9 @@ class CudaCommu:
         active = self.active_gpus
         i_am_active = self.world_rank in active
         if self.current_step == 1:
+            if self.local_hook_num == 1:             # first bucket of step 1: (re)learn the layout from scratch
+                self.bucket_info.clear()
+                self.relay_buffer.clear()
             self.bucket_info.append((size, chunk_bytes, buffer.dtype))
             if self.relay_control and self.relay_mode == RELAY_FORWARD and self._resolve_algo(size, buffer.dtype, active) == "tree":
                 self.relay_buffer.append(torch.zeros(size, dtype=buffer.dtype, device=buffer.device))
