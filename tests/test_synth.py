@@ -149,3 +149,19 @@ def test_multiround_broadcast_milp():
     s.validate(4)
     assert len(s.trees) == 2 and all(t.root == 0 for t in s.trees)
     assert len(schedule_broadcast(8, full_arcs(8), root=3, partitions=1)) == 1    # one hop on a full mesh
+
+
+def test_synth_cli_shape_and_measured_profile(tmp_path):
+    """``python -m adapcc_b200.synth``: nominal server shapes, and the measured 4xB200 profile shipped in topology/."""
+    from adapcc_b200.synth.__main__ import main
+
+    out = tmp_path / "s" / "shape.xml"
+    assert main(["--shape", "4-2", "--policy", "par-trees", "--degree", "2", "--size", "1e6", "--out", str(out)]) == 0
+    s = Strategy.from_file(str(out), 6)
+    s.validate(6)
+    assert len(s.trees) == 2 and {t.root for t in s.trees} == {0, 4}          # one root per server (parity rule)
+    prof = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "topology", "measured_4xB200")
+    if os.path.isdir(prof):
+        out2 = tmp_path / "m.xml"
+        assert main(["--profile-dir", prof, "--policy", "par-trees", "--out", str(out2)]) == 0
+        Strategy.from_file(str(out2), 4).validate(4)
