@@ -330,3 +330,21 @@ def test_api_misuse_is_handled(tmp_path):
     for case in ("allreduce before setup", "double init", "setup twice", "setup other prims", "reduce", "clear unknown prim",
                  "clear", "clear twice", "use after clear"):
         assert f"{case} -> ok" in out, out
+
+
+def test_hook_training_matches_stock_ddp_on_cpu(tmp_path):
+    """Accuracy / precision check (the reference's accuracy benchmark): 30 SGD steps through the AdapCC comm hook end in
+    the same parameters (to fp32 rounding) and the same accuracy as stock DDP gradient averaging — 3 gloo ranks."""
+    import re
+    import subprocess
+
+    mport, cport = _free_ports(2)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr",
+           "127.0.0.1", "--master-port", str(mport), os.path.join(ROOT, "tests", "cpu_convergence_worker.py"), str(tmp_path),
+           str(cport)]
+    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300, env=dict(os.environ, PYTHONPATH=ROOT))
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    rows = re.findall(r"\[rank (\d)\] max param diff ([0-9.e+-]+) acc stock ([0-9.]+) acc hook ([0-9.]+)", r.stdout)
+    assert len(rows) == 3, r.stdout
+    for _, diff, a0, a1 in rows:
+        assert float(diff) < 1e-5 and float(a0) > 0.9 and abs(float(a0) - float(a1)) < 1e-6
