@@ -57,7 +57,10 @@ def init_processes(args):
         dist.init_process_group("gloo", rank=WORLD_RANK, world_size=WORLD_SIZE)
         args.backend = "gloo"
     model, shape, classes = build_model(args.model)
-    model = model.to(dev)
+    # whole-model precision (the reference's accuracy benchmark casts the model with --fp16 / --bfp16,
+    # models/image-classification/accuracy_benchmark.py:93-94,196-199)
+    mdtype = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[args.dtype]
+    model = model.to(dev).to(mdtype)
     loss_fn = nn.CrossEntropyLoss()
 
     AdapCC.init(args, LOCAL_RANK, WORLD_RANK, WORLD_SIZE)
@@ -71,9 +74,9 @@ def init_processes(args):
         if i != 0 and AdapCC.profile_freq and i % AdapCC.profile_freq == 0:
             AdapCC.reconstruct_topology(args, ALLREDUCE)
         t0 = time.time()
-        outputs = ddp_model(torch.randn(args.batch, *shape, device=dev))
+        outputs = ddp_model(torch.randn(args.batch, *shape, device=dev, dtype=mdtype))
         labels = torch.randint(0, classes, [args.batch], device=dev)
-        loss = loss_fn(outputs, labels)
+        loss = loss_fn(outputs.float(), labels)
         optimizer.zero_grad()
         loss.backward()
         optimizer.step()
@@ -101,6 +104,8 @@ if __name__ == "__main__":
     parser.add_argument("--bucket_cap_mb", type=int, default=100)
     parser.add_argument("--heap_mb", type=int, default=0, help=">0: DDP buckets live in the symmetric heap (zero-copy)")
     parser.add_argument("--wire_dtype", type=str, default=None, help="e.g. bfloat16: fp32 buckets travel as bf16")
+    parser.add_argument("--dtype", type=str, default="fp32", choices=["fp32", "fp16", "bf16"],
+                        help="whole-model precision (gradient buckets travel in the same dtype)")
     parser.add_argument("--algo", type=str, default="auto")
     parser.add_argument("--relay_mode", type=str, default="forward", choices=["forward", "bypass"])
     init_processes(parser.parse_args())
