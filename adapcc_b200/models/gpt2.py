@@ -230,6 +230,40 @@ class GPT2DoubleHeads(nn.Module):
         return loss, lm_loss, mc_loss
 
 
+@torch.no_grad()
+def sample_sequence(model: "GPT2DoubleHeads", input_ids: torch.Tensor, token_type_ids: Optional[torch.Tensor] = None,
+                    max_new_tokens: int = 20, temperature: float = 0.7, top_k: int = 0, top_p: float = 0.9,
+                    eos_token: Optional[int] = None, reply_type: Optional[int] = None,
+                    generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Nucleus / top-k sampling of a reply, one token at a time (the decoding loop of the reference's interact.py:
+    ``top_filtering`` + ``sample_sequence``, /root/reference/models/gpt2/interact.py). ``input_ids`` [1, T]; new tokens
+    get ``reply_type`` as their token type when given. No KV cache: a demo / evaluation path, not a serving engine."""
+    ids = input_ids.clone()
+    tt = token_type_ids.clone() if token_type_ids is not None else None
+    vocab = model.cfg.vocab_size
+    for _ in range(max_new_tokens):
+        window = slice(max(0, ids.shape[1] - model.cfg.n_positions), None)
+        h = model.hidden(ids[:, window], tt[:, window] if tt is not None else None)
+        logits = (h[:, -1].float() @ model.wte.weight.float().t())[:, :vocab] / max(temperature, 1e-6)
+        if top_k > 0:
+            kth = torch.topk(logits, min(top_k, vocab)).values[:, -1:]
+            logits = logits.masked_fill(logits < kth, float("-inf"))
+        if 0.0 < top_p < 1.0:
+            srt, idx = torch.sort(logits, descending=True)
+            cum = torch.softmax(srt, -1).cumsum(-1)
+            drop = cum > top_p
+            drop[:, 1:] = drop[:, :-1].clone()                  # keep the first token that crosses the threshold
+            drop[:, 0] = False
+            logits = logits.masked_fill(torch.zeros_like(drop).scatter(1, idx, drop), float("-inf"))
+        nxt = torch.multinomial(torch.softmax(logits, -1), 1, generator=generator)
+        ids = torch.cat([ids, nxt], 1)
+        if tt is not None:
+            tt = torch.cat([tt, torch.full_like(nxt, reply_type if reply_type is not None else int(tt[0, -1]))], 1)
+        if eos_token is not None and int(nxt) == eos_token:
+            break
+    return ids[:, input_ids.shape[1]:]
+
+
 def lm_rows_needed(lm_labels: torch.Tensor, multiple: int = 256) -> int:
     """Capacity for ``GPT2DoubleHeads.lm_row_capacity`` from a (host) label tensor [B, C, T]: the number
     of scored next-token rows, rounded up to ``multiple``."""

@@ -158,3 +158,29 @@ def test_flat_engine_state_dict_roundtrip_on_cpu():
     with pytest.raises(KeyError):
         b.load_state_dict(bad)
     b.load_state_dict(bad, strict=False)
+
+
+def test_gpt2_sampling_respects_top_k_top_p_and_eos():
+    from adapcc_b200.models.gpt2 import sample_sequence
+
+    torch.manual_seed(0)
+    cfg = GPT2Config.tiny()
+    m = GPT2DoubleHeads(cfg).eval()
+    prompt = torch.randint(0, cfg.vocab_size, (1, 9))
+    tt = torch.full_like(prompt, cfg.vocab_size - 4)
+    g = torch.Generator().manual_seed(1)
+    out = sample_sequence(m, prompt, tt, max_new_tokens=7, top_k=5, top_p=0.9, reply_type=cfg.vocab_size - 5, generator=g)
+    assert out.shape == (1, 7) and int(out.max()) < cfg.vocab_size
+    # top_k = 1 is greedy decoding: deterministic and equal to the arg-max continuation
+    a = sample_sequence(m, prompt, tt, max_new_tokens=4, top_k=1, top_p=1.0)
+    b = sample_sequence(m, prompt, tt, max_new_tokens=4, top_k=1, top_p=1.0)
+    assert torch.equal(a, b)
+    h = m.hidden(prompt, tt)
+    first = int((h[:, -1].float() @ m.wte.weight.float().t())[:, :cfg.vocab_size].argmax())
+    assert int(a[0, 0]) == first
+    # stops at EOS
+    c = sample_sequence(m, prompt, tt, max_new_tokens=10, top_k=1, top_p=1.0, eos_token=first)
+    assert c.shape == (1, 1)
+    # longer than the context window: the window slides
+    long = sample_sequence(m, torch.randint(0, cfg.vocab_size, (1, cfg.n_positions)), None, max_new_tokens=3, top_k=1, top_p=1.0)
+    assert long.shape == (1, 3)
