@@ -200,3 +200,23 @@ def test_python_and_native_parsers_agree_under_fuzzing():
             assert nat == py, (py, nat, xml[:300])
             agree += 1
     assert agree > 150
+
+
+def test_native_reader_accepts_every_shipped_and_reference_strategy_file(reference_dir):
+    """csrc/schedule.cpp against all strategy XML files of this repo and (when mounted) of the reference, including the
+    reference's malformed-attribute dialect: same number of trees as the Python reader."""
+    import glob
+
+    from adapcc_b200.runtime.native import native_relay_control
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "strategy", "*.xml")))
+    if reference_dir:
+        files += sorted(glob.glob(os.path.join(reference_dir, "strategy", "*.xml")))
+    assert len(files) >= 10
+    for f in files:
+        xml = open(f).read()
+        s = Strategy.from_xml(xml)
+        world = len(s.ranks())
+        r = native_relay_control(xml, world, 0, s.trees[0].root, list(range(world)))
+        assert r["n_trees"] == len(s.trees), f
