@@ -337,6 +337,13 @@ class CudaCommu:
 
     def update_relay(self, step):
         """called once per iteration before forward: heartbeat + (for relays) data-plane duty"""
+        if getattr(self, "_cleared", False) and step >= 0:
+            # a closure that captured the communicator before reconstruct_topology keeps calling the cleared one:
+            # forward to the live communicator, like cuda_allreduce_hook does (otherwise relay control, straggler
+            # handling and the heartbeat are silently off for the rest of the run)
+            live = self._live()
+            if live is not self:
+                return live.update_relay(step)
         self.step_queue.put(step)
         self.current_step = step
         self.local_hook_num = 0

@@ -89,6 +89,8 @@ class Coordinator:
             st = self._steps[step] = _Step()
             for old in [s for s in self._steps if s < step - self.keep_steps]:
                 del self._steps[old]
+            for old in [s for s in self.arrival_log if s < step - self.keep_steps]:
+                del self.arrival_log[old]                   # same lifetime as the step state (long runs)
         return st
 
     # -- service methods (plain Python signatures; gRPC adapters below) ---------------------
@@ -161,9 +163,15 @@ class Coordinator:
         return pb.hook_response(active_list=self.hook(request.step, request.world_rank))
 
 
-def make_server(coordinator: Coordinator, max_workers: int = 32):
-    """gRPC server bound to ``coordinator.ip:port`` (not started)."""
+def make_server(coordinator: Coordinator, max_workers: Optional[int] = None):
+    """gRPC server bound to ``coordinator.ip:port`` (not started). Every rank holds up to two blocking RPCs per
+    step (``controller_fetch`` until the step is decided, ``hook_fetch`` as leader or waiter), so the pool is sized
+    from the world size: with a fixed pool the controllers of a large job could fill it and starve the hooks that
+    would decide the step (-> a false fault after ``fault_tolerant_time``)."""
     import grpc
+
+    if max_workers is None:
+        max_workers = max(32, 2 * coordinator.world_size + 8)
 
     handlers = {
         "controller_fetch": grpc.unary_unary_rpc_method_handler(

@@ -66,7 +66,6 @@ int launch_direct(int algo, int blocks, cudaStream_t s, const DevComm& dc, const
     allreduce_direct_kernel<U, W, OP, NVLS, 2><<<blocks, kThreads, 0, s>>>(dc, i, o, n, scale, flags, root);
     CUDA_TRY(cudaGetLastError());
     count_launch();
-  count_launch();
     return 0;
   }
   const int na = dc.n_active;
@@ -198,6 +197,8 @@ int CommContext::fill_comm(const std::vector<int>& parts, const Window& w, void*
   dc.err = (uint32_t*)(d_state_ + kStateErr);
   dc.seq = (unsigned long long*)(d_state_ + kStateSeq);
   dc.timeout_ns = tun.timeout_ms > 0 ? (unsigned long long)tun.timeout_ms * 1000000ull : 0ull;
+  dc.op_advance = 1;
+  dc.item_base = 0;
   return 0;
 }
 
@@ -312,6 +313,7 @@ int CommContext::reduce(const void* in, void* out, long long count, int dtype, i
   while (done < count) {
     const long long n = std::min(count - done, cap_elems);
     const long long npacks = (n + epp - 1) / epp;
+    dc.op_advance = (done + n >= count) ? 1 : 0;      // the op sequence number moves once per logical op
     int blocks = (int)std::min<long long>((npacks + (long long)kThreads * kUnroll - 1) / ((long long)kThreads * kUnroll),
                                           (long long)std::min(tun.max_blocks, kMaxBlocks));
     if (blocks < 1) blocks = 1;
@@ -376,6 +378,7 @@ int CommContext::broadcast(void* buf, long long count, int dtype, int root, cons
   while (done < count) {
     const long long n = std::min(count - done, cap_elems);
     const long long npacks = (n + epp - 1) / epp;
+    dc.op_advance = (done + n >= count) ? 1 : 0;
     int blocks = (int)std::min<long long>((npacks + (long long)kThreads * kUnroll - 1) / ((long long)kThreads * kUnroll),
                                           (long long)std::min(tun.max_blocks, kMaxBlocks));
     if (blocks < 1) blocks = 1;
@@ -384,9 +387,7 @@ int CommContext::broadcast(void* buf, long long count, int dtype, int root, cons
     int rc = ADAPCC_DISPATCH_TYPES(dtype, wire, {
       broadcast_direct_kernel<U, W><<<blocks, kThreads, 0, stream>>>(dc, (U*)p, n, root_index, use_mc, flags);
       CUDA_TRY(cudaGetLastError());
-    count_launch();
       count_launch();
-  count_launch();
       return 0;
     });
     if (rc) return rc;
@@ -505,6 +506,11 @@ int CommContext::tree_collective(int prim, const void* in, void* out, long long 
     int lanes = (int)std::min<long long>(items, (long long)std::min(tun.tree_blocks, kMaxBlocks) / 2);
     if (lanes < 1) lanes = 1;
     const int blocks = 2 * lanes;
+    dc.op_advance = (done + n >= count) ? 1 : 0;
+    if (dc.item_base + (unsigned long long)((items + lanes - 1) / lanes) >= (1ull << 24)) {
+      set_error("tree collective: more than 2^24 pipeline items in one op (raise the chunk size or staging_mb)");
+      return -1;
+    }
     const char* pin = (const char*)in + (size_t)done * esize;
     char* pout = (char*)out + (size_t)done * esize;
     int rc = ADAPCC_DISPATCH_TYPES(dtype, wire, {
@@ -513,13 +519,12 @@ int CommContext::tree_collective(int prim, const void* in, void* out, long long 
       else
         tree_collective_kernel<U, W, SUM><<<blocks, kThreads, 0, stream>>>(dc, plan, (const U*)pin, (U*)pout, n, scale);
       CUDA_TRY(cudaGetLastError());
-    count_launch();
       count_launch();
-  count_launch();
       return 0;
     });
     if (rc) return rc;
     done += n;
+    dc.item_base += (unsigned long long)((items + lanes - 1) / lanes);   // later pieces: strictly larger tokens
   }
   return 0;
 }

@@ -30,6 +30,11 @@ struct DevComm {
   uint32_t* ticket;                // local: last-block ticket
   uint32_t* err;                   // local: sticky error word (timeouts)
   unsigned long long timeout_ns;   // spin timeout (0 = wait forever)
+  // A logical op larger than the staging window runs as back-to-back pieces (one launch each). The op
+  // sequence number must move exactly ONCE per logical op on every rank (a rank that sits an op out runs one
+  // skip_op), so only the last piece advances it; tree tokens stay monotonic through `item_base`.
+  int op_advance;                  // 1 on the last (or only) piece of an op, 0 on earlier pieces
+  unsigned long long item_base;    // tree kernels: pipeline items consumed by earlier pieces of this op
 };
 
 // ----------------------------------------------------------------------------------
@@ -118,7 +123,8 @@ __device__ __forceinline__ void block_barrier(const DevComm& c, BarrierState& b)
 // Every kernel ends with this: persist the pair epochs and let the last block to finish
 // advance the context's op sequence number (device-side, so the kernels stay CUDA-graph
 // capturable: no host-computed epoch is baked into the launch).
-__device__ __forceinline__ void finish_op(const DevComm& c, const BarrierState& b, unsigned advance = 1) {
+__device__ __forceinline__ void finish_op(const DevComm& c, const BarrierState& b, int advance = -1) {
+  if (advance < 0) advance = c.op_advance;
   if (b.peer >= 0) c.bar_epoch[blockIdx.x * kMaxRanks + b.peer] = b.epoch;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -126,7 +132,7 @@ __device__ __forceinline__ void finish_op(const DevComm& c, const BarrierState& 
     const uint32_t t = atomicAdd(c.ticket, 1u);
     if (t == gridDim.x - 1) {
       *c.ticket = 0;
-      *c.seq = *c.seq + advance;
+      *c.seq = *c.seq + (unsigned long long)advance;
     }
   }
 }

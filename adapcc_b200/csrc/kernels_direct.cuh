@@ -97,6 +97,28 @@ __device__ __forceinline__ void stage_out(const Partition& P, U* __restrict__ ou
   }
 }
 
+// Zero-copy tensors need not be a whole number of 16-byte packs (a slice of a heap tensor, a DDP bucket with an
+// odd element count). The last pack is then PARTIAL: it is loaded as 16 bytes (the bytes past the tensor are inside
+// the symmetric heap, so the read is safe and its lanes are simply dropped) but must be stored element by element,
+// or every peer's memory right after the tensor would be overwritten with reduced neighbour data.
+struct TailPack {
+  long long pack;    // global index of the partial last pack, -1 when the message is a whole number of packs
+  int elems;         // valid wire elements in it
+};
+template <typename W>
+__device__ __forceinline__ TailPack tail_of(long long n, bool zero_copy) {
+  constexpr int kEpp = WireTraits<W>::kEpp;
+  TailPack t;
+  t.elems = (int)(n % kEpp);
+  t.pack = (zero_copy && t.elems) ? n / kEpp : -1;
+  return t;
+}
+template <typename W>
+__device__ __forceinline__ void st_tail(char* dst, const float* f, int elems) {
+  W* d = reinterpret_cast<W*>(dst);
+  for (int i = 0; i < elems; ++i) d[i] = from_float<W>(f[i]);
+}
+
 // ----------------------------------------------------------------------------------
 // phase-1 bodies, specialised on NR = upper bound of participants (2/4/8/16) so that
 // NR x UN = 16 independent 128-bit peer loads are in flight per thread: NVLink round trips
@@ -149,7 +171,7 @@ __device__ __forceinline__ void one_shot_phase1(const DevComm& c, long long npac
 template <typename W, int OP, int NR>
 __device__ __forceinline__ void two_shot_phase1(const DevComm& c, long long base, long long cnt,
                                                 bool zero_copy, float scale, bool root_only, int root,
-                                                SubGrid g = SubGrid()) {
+                                                SubGrid g = SubGrid(), TailPack tail = TailPack{-1, 0}) {
   constexpr int kEpp = WireTraits<W>::kEpp;
   constexpr int UN = 16 / NR;
   const int na = c.n_active, me = c.my_index;
@@ -194,7 +216,14 @@ __device__ __forceinline__ void two_shot_phase1(const DevComm& c, long long base
           for (int i = 0; i < kEpp; ++i) acc[i] *= scale;
         }
         const uint4 r = pack<W>(acc);
-        if (root_only) {
+        if (base + j == tail.pack) {           // partial last pack of a zero-copy tensor: bounded stores
+          if (root_only) {
+            st_tail<W>(root_ptr + off, acc, tail.elems);
+          } else {
+            for (int a = 0; a < NR; ++a)
+              if (a < na) st_tail<W>(peers[a] + off, acc, tail.elems);
+          }
+        } else if (root_only) {
           st16(root_ptr + off, r);
         } else {
 #pragma unroll
@@ -208,7 +237,8 @@ __device__ __forceinline__ void two_shot_phase1(const DevComm& c, long long base
 
 template <typename W, int OP>
 __device__ __forceinline__ void nvls_phase1(const DevComm& c, long long base, long long cnt, bool zero_copy,
-                                            float scale, bool root_only, int root, SubGrid g = SubGrid()) {
+                                            float scale, bool root_only, int root, SubGrid g = SubGrid(),
+                                            TailPack tail = TailPack{-1, 0}) {
   constexpr int kEpp = WireTraits<W>::kEpp;
   constexpr int UN = 8;
   const long long stride = (long long)g.nb * kThreads;
@@ -231,7 +261,15 @@ __device__ __forceinline__ void nvls_phase1(const DevComm& c, long long base, lo
           for (int i = 0; i < kEpp; ++i) f[i] *= scale;
           v[u] = pack<W>(f);
         }
-        if (root_only) st16(root_ptr + (base + j) * 16, v[u]);
+        if (base + j == tail.pack) {           // partial last pack: unicast, element by element
+          float f[kEpp];
+          unpack<W>(v[u], f);
+          if (root_only) {
+            st_tail<W>(root_ptr + (base + j) * 16, f, tail.elems);
+          } else {
+            for (int a = 0; a < c.n_active; ++a) st_tail<W>(c.data[c.active_ranks[a]] + (base + j) * 16, f, tail.elems);
+          }
+        } else if (root_only) st16(root_ptr + (base + j) * 16, v[u]);
         else mc_st16(c.mc_data + (base + j) * 16, v[u]);
       }
     }
@@ -272,8 +310,9 @@ allreduce_direct_kernel(const __grid_constant__ DevComm c, const U* __restrict__
     block_barrier(c, epoch);
   } else {
     const long long base = P.slice_begin(me), cnt = P.slice_count(me);
-    if (ALGO == TWO_SHOT) two_shot_phase1<W, OP, NR>(c, base, cnt, zero_copy, scale, root_only, root);
-    else nvls_phase1<W, OP>(c, base, cnt, zero_copy, scale, root_only, root);
+    const TailPack tail = tail_of<W>(n, zero_copy);
+    if (ALGO == TWO_SHOT) two_shot_phase1<W, OP, NR>(c, base, cnt, zero_copy, scale, root_only, root, SubGrid(), tail);
+    else nvls_phase1<W, OP>(c, base, cnt, zero_copy, scale, root_only, root, SubGrid(), tail);
     block_barrier(c, epoch);
     // ---- phase 2: hand the result back to the caller ------------------------------
     if (!zero_copy && (!root_only || me == root))
@@ -299,6 +338,7 @@ broadcast_direct_kernel(const __grid_constant__ DevComm c, U* __restrict__ buf, 
   P.nslices = 1;
   P.pps = P.npacks;
   const long long stride = (long long)gridDim.x * kThreads;
+  const TailPack tail = tail_of<W>(n, zero_copy);
 
   // everyone must have entered the op before the root overwrites their window
   block_barrier(c, epoch);
@@ -322,7 +362,12 @@ broadcast_direct_kernel(const __grid_constant__ DevComm c, U* __restrict__ buf, 
       for (int u = 0; u < kUnroll; ++u) {
         const long long j = j0 + u * stride;
         if (j < P.npacks) {
-          if (use_mc) {
+          if (j == tail.pack) {                // partial last pack of a zero-copy tensor
+            float f[kEpp];
+            unpack<W>(v[u], f);
+            for (int a = 0; a < na; ++a)
+              if (a != me) st_tail<W>(c.data[c.active_ranks[a]] + j * 16, f, tail.elems);
+          } else if (use_mc) {
             mc_st16(c.mc_data + j * 16, v[u]);
           } else {
 #pragma unroll

@@ -114,7 +114,7 @@ allreduce_pipelined_kernel(const __grid_constant__ DevComm c, PipeState* __restr
       for (int i = 0; i < kMaxPieces; ++i) { ps->in_ready[i] = 0; ps->out_ready[i] = 0; }
       __threadfence();
       *c.ticket = 0;
-      *c.seq = *c.seq + 1;
+      *c.seq = *c.seq + (unsigned long long)c.op_advance;
     }
   }
 }

@@ -141,7 +141,7 @@ __device__ __forceinline__ void tree_collective_body(const DevComm& c, const Tre
     long long pc = plan.slice_begin[t + 1] - p0;
     if (pc <= 0) continue;
     if (pc > plan.chunk_packs) pc = plan.chunk_packs;
-    const unsigned long long token = (q << 24) | (m + 1);
+    const unsigned long long token = (q << 24) | (c.item_base + m + 1);
     const TreeRole& role = plan.role[t];
     const bool is_root = role.parent < 0;
     const int nc = role.n_children;
@@ -253,7 +253,7 @@ tree_relay_persistent_kernel(const __grid_constant__ DevComm c, const RelayWork*
     tree_collective_body<W, W, OP>(c, work[i].plan, (const W*)nullptr, (W*)nullptr, work[i].n, work[i].scale,
                                    q0 + (unsigned long long)i, epoch, work[i].lanes);
   }
-  finish_op(c, epoch, (unsigned)n_work);
+  finish_op(c, epoch, n_work);
 }
 
 // Keeps a non-participating rank's op sequence number in step with the others.

@@ -23,7 +23,8 @@ __device__ __forceinline__ void online_combine(float& m, float& s, float m2, flo
 
 __global__ void __launch_bounds__(512)
 fused_ce_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restrict__ labels,
-                float* __restrict__ row_loss, int vocab, int stride) {
+                float* __restrict__ row_loss, int vocab, int stride, const float* __restrict__ grad_scale) {
+  const float gs = grad_scale ? *grad_scale : 1.f;       // d(total loss)/d(row loss), folded into the gradient
   const int row = blockIdx.x;
   __nv_bfloat16* p = logits + (long long)row * stride;
   const long long label = labels[row];
@@ -78,8 +79,8 @@ fused_ce_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restrict_
     for (int i = 0; i < 4; ++i) {
       float a = __uint_as_float(w[i] << 16), b = __uint_as_float(w[i] & 0xffff0000u);
       const int c = v * 8 + 2 * i;
-      float ga = (valid && c < vocab) ? __expf(a - m) * inv - (c == label ? 1.f : 0.f) : 0.f;
-      float gb = (valid && c + 1 < vocab) ? __expf(b - m) * inv - (c + 1 == label ? 1.f : 0.f) : 0.f;
+      float ga = (valid && c < vocab) ? (__expf(a - m) * inv - (c == label ? 1.f : 0.f)) * gs : 0.f;
+      float gb = (valid && c + 1 < vocab) ? (__expf(b - m) * inv - (c + 1 == label ? 1.f : 0.f)) * gs : 0.f;
       __nv_bfloat162 r = __floats2bfloat162_rn(ga, gb);
       o[i] = *reinterpret_cast<uint32_t*>(&r);
     }
@@ -93,7 +94,8 @@ fused_ce_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restrict_
 // pass 3 gradient = e / sum - onehot. ncu on v1 showed it SFU/ALU-bound (83 % SM, 32 % DRAM).
 __global__ void __launch_bounds__(512)
 fused_ce_smem_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restrict__ labels,
-                     float* __restrict__ row_loss, int vocab, int stride) {
+                     float* __restrict__ row_loss, int vocab, int stride, const float* __restrict__ grad_scale) {
+  const float gs = grad_scale ? *grad_scale : 1.f;
   extern __shared__ uint4 srow[];
   const int row = blockIdx.x;
   __nv_bfloat16* p = logits + (long long)row * stride;
@@ -159,14 +161,14 @@ fused_ce_smem_kernel(__nv_bfloat16* __restrict__ logits, const long long* __rest
     row_loss[row] = valid ? (__logf(ss) + m - xl) : 0.f;
   }
   __syncthreads();
-  const float inv = valid ? 1.f / bcast[1] : 0.f;
+  const float inv = valid ? gs / bcast[1] : 0.f;
   for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
     float e[8];
     unpack<__nv_bfloat16>(srow[v], e);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = v * 8 + i;
-      e[i] = e[i] * inv - ((valid && c == label) ? 1.f : 0.f);
+      e[i] = e[i] * inv - ((valid && c == label) ? gs : 0.f);
     }
     st16(reinterpret_cast<uint4*>(p) + v, pack<__nv_bfloat16>(e));
   }
@@ -174,8 +176,10 @@ fused_ce_smem_kernel(__nv_bfloat16* __restrict__ logits, const long long* __rest
 
 }  // namespace adapcc
 
-extern "C" int adapcc_fused_ce(void* logits, const long long* labels, float* row_loss, int rows, int vocab,
-                               int stride, void* stream) {
+// grad_scale (optional device scalar): the gradient written into `logits` is multiplied by it (e.g. 1 / #scored
+// rows of a mean loss), so the GEMMs that consume it produce final gradients; row losses stay unscaled.
+extern "C" int adapcc_fused_ce_scaled(void* logits, const long long* labels, float* row_loss, int rows, int vocab,
+                                      int stride, const float* grad_scale, void* stream) {
   using namespace adapcc;
   if (rows <= 0) return 0;
   if (stride % 8 != 0 || (reinterpret_cast<uintptr_t>(logits) & 15)) {
@@ -193,10 +197,16 @@ extern "C" int adapcc_fused_ce(void* logits, const long long* labels, float* row
   const char* force = getenv("ADAPCC_CE_V1");
   if (smem_ok && smem <= 200 * 1024 && !(force && atoi(force)))
     fused_ce_smem_kernel<<<rows, 512, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)logits, labels, row_loss, vocab,
-                                                                    stride);
+                                                                    stride, grad_scale);
   else
-    fused_ce_kernel<<<rows, 512, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)logits, labels, row_loss, vocab, stride);
+    fused_ce_kernel<<<rows, 512, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)logits, labels, row_loss, vocab, stride,
+                                                            grad_scale);
   CUDA_TRY(cudaGetLastError());
   count_launch();
   return 0;
+}
+
+extern "C" int adapcc_fused_ce(void* logits, const long long* labels, float* row_loss, int rows, int vocab,
+                               int stride, void* stream) {
+  return adapcc_fused_ce_scaled(logits, labels, row_loss, rows, vocab, stride, nullptr, stream);
 }

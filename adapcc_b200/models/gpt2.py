@@ -97,26 +97,40 @@ class Block(nn.Module):
         return x + self._mlp(self.ln_2(x))
 
 
+def use_sink(p) -> bool:
+    from ..ops.layers import _sink
+    return p.is_cuda and _sink(p) is not None
+
+
 class _ChunkedLMLoss(torch.autograd.Function):
     """sum over rows of CE(h @ W^T, labels), ``chunk`` rows at a time. The backward of every chunk
     is produced inside the forward pass (fused softmax-CE kernel overwrites the bf16 logits with
     their gradient), so logits never outlive a chunk and are touched twice instead of ~8 times."""
 
     @staticmethod
-    def forward(ctx, h, weight, labels, chunk, vocab):
+    def forward(ctx, h, weight, labels, chunk, vocab, scale=None):
+        """``scale`` (1-element fp32 device tensor or None): the result is ``scale * sum of row losses`` and the
+        gradients produced here already contain it — the caller promises that the returned value enters the total
+        loss with coefficient exactly 1 (GPT2DoubleHeads.forward does). That is what allows the weight gradient to be
+        written straight into the engine's flat gradient buffer during the forward pass (``weight`` carries a grad sink,
+        ops/layers.py::_sink): no 77 MB ``grad_w * g`` and no 77 MB accumulate kernel in the backward."""
         n = h.shape[0]
         use_kernel = h.is_cuda and h.dtype == torch.bfloat16 and weight.shape[0] % 8 == 0
         grad_h = torch.empty_like(h)
         grad_w = None
         total = torch.zeros((), dtype=torch.float32, device=h.device)
+        direct = False
         if use_kernel:
             from ..ops import fused_ce_
+            from ..ops.layers import _sink
+            direct = (scale is not None and _sink(weight) is not None and weight.grad.dtype == h.dtype
+                      and ctx.needs_input_grad[1])
         for s in range(0, n, chunk):
             hs = h[s:s + chunk]
             ls = labels[s:s + chunk]
             logits = hs @ weight.t()
             if use_kernel:
-                total += fused_ce_(logits, ls, vocab).sum()
+                total += fused_ce_(logits, ls, vocab, grad_scale=scale).sum()
                 g = logits                                         # now d loss / d logits (bf16)
             else:                                                  # CPU / fp32 reference path
                 lf = logits.float()
@@ -127,23 +141,45 @@ class _ChunkedLMLoss(torch.autograd.Function):
                 total += ((lse - tgt) * valid).sum()
                 p = torch.softmax(lf, dim=-1)
                 p.scatter_add_(1, ls.clamp(min=0).unsqueeze(1), -torch.ones_like(p[:, :1]))
-                g = (p * valid.unsqueeze(1)).to(h.dtype)
+                g = p * valid.unsqueeze(1)
+                if scale is not None:
+                    g = g * scale
+                g = g.to(h.dtype)
             torch.mm(g, weight, out=grad_h[s:s + chunk])
             # dW accumulates across chunks inside the GEMM (fp32 accumulator, beta = 1 epilogue) — an
             # fp32 side buffer cost ~1 GB of extra HBM traffic per chunk at vocab 50304
-            if grad_w is None:
+            if direct:
+                if s == 0:
+                    torch.mm(g.t(), hs, out=weight.grad)           # the flat-buffer view (zeroed at step start)
+                else:
+                    weight.grad.addmm_(g.t(), hs)
+            elif grad_w is None:
                 grad_w = g.t() @ hs
             else:
                 grad_w.addmm_(g.t(), hs)
-        if grad_w is None:
-            grad_w = torch.zeros_like(weight)
-        ctx.save_for_backward(grad_h, grad_w)
+        if scale is not None:
+            total = total * scale.reshape(())
+        ctx.direct, ctx.weight = direct, weight
+        if direct:
+            ctx.save_for_backward(grad_h)
+        else:
+            if grad_w is None:
+                grad_w = torch.zeros_like(weight)
+            ctx.save_for_backward(grad_h, grad_w)
         return total
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.direct:                       # unit upstream gradient by contract; dW is already in weight.grad
+            return ctx.saved_tensors[0], None, None, None, None, None
         grad_h, grad_w = ctx.saved_tensors
-        return grad_h * g.to(grad_h.dtype), grad_w * g.to(grad_w.dtype), None, None, None
+        gw = grad_w * g.to(grad_w.dtype)
+        if use_sink(ctx.weight):
+            # the table's gradient is owned by a sink (its LAST writer, the fused embedding backward, reports it):
+            # autograd must not see a gradient for it, or the engine would count the parameter twice
+            ctx.weight.grad.add_(gw)
+            gw = None
+        return grad_h * g.to(grad_h.dtype), gw, None, None, None, None
 
 
 class GPT2DoubleHeads(nn.Module):
@@ -164,6 +200,13 @@ class GPT2DoubleHeads(nn.Module):
         self.lm_row_capacity = 0
         # residual adds fused into the following LayerNorm (fwd) / its input gradient (bwd)
         self.fuse_add_ln = os.environ.get("ADAPCC_FUSE_ADD_LN", "0") == "1"
+        # wte[ids] + wpe[pos] + wte[token types] as one kernel, sort-free fp32-accumulating backward
+        # (csrc/ops_embed.cu); the flat engine gives both tables a gradient sink (parallel/engine.py)
+        self.fused_embed = os.environ.get("ADAPCC_FUSED_EMBED", "1") != "0"
+        if self.fused_embed:
+            self.wte.weight._adapcc_embed_table = True
+            self.wpe.weight._adapcc_embed_table = True
+        self._pos_cache = {}
         self.apply(self._init)
         for blk in self.h:                                  # GPT-2 residual-projection scaling
             for lin in (blk.c_proj, blk.c_proj2):
@@ -180,10 +223,20 @@ class GPT2DoubleHeads(nn.Module):
 
     def hidden(self, input_ids: torch.Tensor, token_type_ids: Optional[torch.Tensor]) -> torch.Tensor:
         N, T = input_ids.shape
-        pos = torch.arange(T, device=input_ids.device)
-        x = self.wte(input_ids) + self.wpe(pos)[None]
-        if token_type_ids is not None:
-            x = x + self.wte(token_type_ids)
+        if (self.fused_embed and input_ids.is_cuda and self.wte.weight.dtype == torch.bfloat16
+                and self.wpe.weight.dtype == torch.bfloat16):
+            from ..ops import fused_embedding_sum
+            key = (N, T, input_ids.device)
+            pos = self._pos_cache.get(key)
+            if pos is None:
+                pos = self._pos_cache[key] = torch.arange(T, device=input_ids.device).repeat(N)
+            lookups = [(0, input_ids), (1, pos)] + ([(0, token_type_ids)] if token_type_ids is not None else [])
+            x = fused_embedding_sum([self.wte.weight, self.wpe.weight], lookups).view(N, T, -1)
+        else:
+            pos = torch.arange(T, device=input_ids.device)
+            x = self.wte(input_ids) + self.wpe(pos)[None]
+            if token_type_ids is not None:
+                x = x + self.wte(token_type_ids)
         if self.fuse_add_ln:
             delta = None
             for blk in self.h:
@@ -216,17 +269,22 @@ class GPT2DoubleHeads(nn.Module):
                 order = torch.argsort((shift_l < 0).to(torch.int8), stable=True)[:cap]
                 shift_h = shift_h.index_select(0, order)
                 shift_l = shift_l.index_select(0, order)
-            lm_loss = _ChunkedLMLoss.apply(shift_h, self.wte.weight, shift_l, self.cfg.lm_chunk_rows,
-                                           self.cfg.vocab_size) / n_valid.clamp(min=1)
+            # the mean's 1/n and lm_coef travel INTO the fused CE kernel, so the LM term enters `loss` with
+            # coefficient 1 (the contract of _ChunkedLMLoss's direct weight-gradient path)
+            scale = (lm_coef / n_valid.clamp(min=1).to(torch.float32)).reshape(1)
+            lm_term = _ChunkedLMLoss.apply(shift_h, self.wte.weight, shift_l, self.cfg.lm_chunk_rows,
+                                           self.cfg.vocab_size, scale)
+            lm_loss = lm_term / lm_coef if lm_coef != 0 else lm_term
             if compact:
                 # a batch with more scored rows than the capacity must not train silently on a subset
                 lm_loss = torch.where(n_valid > cap, torch.full_like(lm_loss, float("nan")), lm_loss)
+                lm_term = torch.where(n_valid > cap, torch.full_like(lm_term, float("nan")), lm_term)
         if mc_token_ids is not None and mc_labels is not None:
             idx = mc_token_ids.reshape(B * C, 1, 1).expand(-1, 1, h.shape[-1])
             cls_h = h.gather(1, idx).squeeze(1)                               # [B*C, D]
             mc_logits = self.mc_head(cls_h).view(B, C).float()
             mc_loss = F.cross_entropy(mc_logits, mc_labels)
-        loss = lm_coef * lm_loss + mc_coef * mc_loss
+        loss = (lm_term if lm_labels is not None else zero) + mc_coef * mc_loss
         return loss, lm_loss, mc_loss
 
 

@@ -168,6 +168,15 @@ class FlatDataParallel:
                         sink = _GradSink(self, index[id(p)])
                         p._adapcc_grad_sink = sink
                         self._sinks.append(sink)
+            # embedding tables (models mark them `_adapcc_embed_table`): the fused embedding backward adds its rows
+            # straight into the table's flat-buffer gradient view — which may already hold the tied LM head's dW,
+            # written during the forward pass (models/gpt2.py::_ChunkedLMLoss) — and reports it done; it is the
+            # last op of the backward pass, so the bucket launches right after it
+            for p in params:
+                if getattr(p, "_adapcc_embed_table", False) and p.dtype == param_dtype and id(p) not in uses:
+                    sink = _GradSink(self, index[id(p)])
+                    p._adapcc_grad_sink = sink
+                    self._sinks.append(sink)
         self.direct_grads = bool(self._sinks)
         self.comm_stream = torch.cuda.Stream(device=dev, priority=-1) if dev.type == "cuda" else None
         self._graph = None

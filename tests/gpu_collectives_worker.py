@@ -182,6 +182,69 @@ def main():
                 comm.check()
                 check(f"zero-copy allreduce {algo} {dtype} n={n}", t,
                       ref_reduce(world, n, dtype, seed, "avg", all_ranks), dtype, None, world)
+    # ---- zero-copy on a tensor that is NOT a whole number of 16-byte packs (a slice of a heap tensor): the partial
+    # last pack must be stored element-wise — the bytes right after the slice belong to somebody else ----------------
+    for dtype in [torch.float32, torch.bfloat16]:
+        for algo in [a for a in algos if a != "one_shot"]:
+            for n in [5, 4099, (1 << 18) + 3]:
+                seed += 1
+                comm.heap_reset()
+                whole = comm.symm_empty(n + 64, dtype)
+                whole.fill_(-7.0)
+                t = whole[:n]
+                t.copy_(gen(rank, n, dtype, seed).to(dev))
+                torch.cuda.synchronize()
+                dist.barrier()
+                comm.all_reduce(t, op="sum", algo=algo)
+                comm.check()
+                check(f"zero-copy tail allreduce {algo} {dtype} n={n}", t,
+                      ref_reduce(world, n, dtype, seed, "sum", all_ranks), dtype, None, world)
+                check(f"zero-copy tail guard {algo} {dtype} n={n}", whole[n:], torch.full((64,), -7.0), torch.float32, None, 1)
+                dist.barrier()
+        seed += 1
+        n = 4099
+        comm.heap_reset()
+        whole = comm.symm_empty(n + 64, dtype)
+        whole.fill_(-7.0)
+        t = whole[:n]
+        t.copy_(gen(rank, n, dtype, seed).to(dev))
+        torch.cuda.synchronize()
+        dist.barrier()
+        comm.broadcast(t, root=world - 1)
+        comm.check()
+        check(f"zero-copy tail broadcast {dtype}", t, gen(world - 1, n, dtype, seed).float(), dtype, None, 1)
+        check(f"zero-copy tail broadcast guard {dtype}", whole[n:], torch.full((64,), -7.0), torch.float32, None, 1)
+        dist.barrier()
+    # ---- op sequence numbers stay in step when an op is split into staging-window pieces on the ranks that take
+    # part while a non-participant runs one skip (small window, partial active set, then a tree op) -------------------
+    if world >= 3:
+        small = NativeComm(unique_name("small"), rank, world, local, staging_bytes=1 << 20, heap_bytes=0)
+        small.load_strategy("<trees>" + "".join(
+            "<root id='%d' ip='h'>%s</root>" % (o[0], "".join("<gpu id='%d' ip='h'>" % r for r in o[1:]) + "</gpu>" * (world - 1))
+            for o in (list(range(world)), list(reversed(range(world))))) + "</trees>")
+        act = [0, world - 1]
+        for rep in range(2):
+            seed += 1
+            n = (5 << 18) + 11                                   # 5.2 MB of fp32: 6 pieces through a 1 MB window
+            x = gen(rank, n, torch.float32, seed).to(dev)
+            small.all_reduce(x, op="sum", algo="two_shot", active=act)
+            small.check()
+            want = ref_reduce(world, n, torch.float32, seed, "sum", act) if rank in act else gen(rank, n, torch.float32, seed)
+            check(f"pieces + partial active set (rep {rep})", x, want, torch.float32, None, 2)
+            seed += 1
+            y = gen(rank, 70001, torch.float32, seed).to(dev)
+            small.tree_collective(ALLREDUCE, y, op="sum", chunk_bytes=4096)
+            small.check()
+            check(f"tree op after split op (rep {rep})", y, ref_reduce(world, 70001, torch.float32, seed, "sum", all_ranks),
+                  torch.float32, None, world * 2)
+            seed += 1
+            z = gen(rank, (3 << 18) + 5, torch.float32, seed).to(dev)    # tree op itself split into pieces
+            small.tree_collective(ALLREDUCE, z, op="sum", chunk_bytes=65536)
+            small.check()
+            check(f"tree op in pieces (rep {rep})", z, ref_reduce(world, (3 << 18) + 5, torch.float32, seed, "sum", all_ranks),
+                  torch.float32, None, world * 2)
+        dist.barrier()
+        small.close()
     # ---- reduce-to-root and broadcast (direct) ---------------------------------------
     for root in sorted({0, world - 1}):
         for algo in algos:
@@ -458,6 +521,33 @@ def main():
                 print("[sweep] %10d B " % nbytes + " ".join(
                     f"{k}={v * 1e6:7.1f}us({nbytes * f / v / 1e9:6.1f})" for k, v in row.items() if k != "bytes"),
                     flush=True)
+        # reduce / broadcast / all-to-all next to NCCL (nccl-tests' reduce, broadcast and alltoall,
+        # /root/reference/nccl-perf/benchmark/src/{reduce,broadcast,alltoall}.cu; busbw factor 1, resp. (n-1)/n)
+        for nbytes in [1 << p for p in range(10, 29, 3 if args.quick else 2)]:
+            n = nbytes // 4
+            x = torch.randn(n, device=dev)
+            iters = 40 if nbytes <= (1 << 22) else (10 if nbytes <= (1 << 26) else 4)
+            row = {"bytes": nbytes, "prims": 1}
+            row["reduce_nccl"] = timeit(lambda: dist.reduce(x, dst=0), iters)
+            row["reduce"] = timeit(lambda: comm.reduce(x, root=0, op="sum"), iters)
+            row["bcast_nccl"] = timeit(lambda: dist.broadcast(x, src=0), iters)
+            row["bcast"] = timeit(lambda: comm.broadcast(x, root=0), iters)
+            comm.heap_reset()
+            if nbytes <= comm.heap_bytes:
+                hz = comm.symm_empty(n, torch.float32)
+                row["reduce_zc"] = timeit(lambda: comm.reduce(hz, root=0, op="sum"), iters)
+                row["bcast_zc"] = timeit(lambda: comm.broadcast(hz, root=0), iters)
+            if n % world == 0 and nbytes <= (128 << 20):
+                y = torch.empty_like(x)
+                row["a2a_nccl"] = timeit(lambda: dist.all_to_all_single(y, x), iters)
+                row["a2a"] = timeit(lambda: comm.all_to_all(x, out=y), iters)
+            comm.check()
+            results.append(row)
+            if rank == 0:
+                fa = (world - 1) / world
+                print("[prims] %10d B " % nbytes + " ".join(
+                    f"{k}={v * 1e6:7.1f}us({nbytes * (fa if k.startswith('a2a') else 1.0) / v / 1e9:6.1f})"
+                    for k, v in row.items() if k not in ("bytes", "prims")), flush=True)
         # CTA-count sensitivity at large sizes (zero-copy paths)
         for nbytes in [1 << 24, 1 << 26]:
             n = nbytes // 4

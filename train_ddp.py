@@ -70,9 +70,11 @@ def init_processes(args):
     optimizer = optim.SGD(ddp_model.parameters(), lr=0.001)
 
     for i in range(args.steps):
-        AdapCC.communicator.update_relay(step=i)
+        # reconstruct BEFORE the step's heartbeat: a heartbeat sent to the old coordinator would never be answered
+        # (no hook fires for it), so its controller thread would sit in the RPC until clear() gave up on the join
         if i != 0 and AdapCC.profile_freq and i % AdapCC.profile_freq == 0:
             AdapCC.reconstruct_topology(args, ALLREDUCE)
+        AdapCC.communicator.update_relay(step=i)
         t0 = time.time()
         outputs = ddp_model(torch.randn(args.batch, *shape, device=dev, dtype=mdtype))
         labels = torch.randint(0, classes, [args.batch], device=dev)
