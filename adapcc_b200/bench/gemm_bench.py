@@ -68,6 +68,17 @@ def main() -> int:
         err = float((out.float() - ref.float()).abs().max())
         add(f"tcgen05 variant {v}: gelu(xW^T+b), no pre", lambda v=v: linear_act(x, w, b, "gelu", variant=v), err)
         add(f"tcgen05 variant {v}: gelu(xW^T+b) + pre", lambda v=v: linear_act(x, w, b, "gelu", save_pre=True, variant=v))
+        if v == 3 and a.n % 256 == 0:
+            # the MLP backward: dH = (dY . W2) * gelu'(pre) (+ the up-projection's bias gradient = column sums of dH)
+            aux = ref_pre
+            cs = torch.zeros(a.n, dtype=torch.float32, device=dev)
+            add("cuBLAS matmul + torch gelu_backward kernel",
+                lambda: torch.ops.aten.gelu_backward(x @ w.t(), aux, approximate="tanh"))
+            add("cuBLAS matmul + gelu_backward + colsum kernels",
+                lambda: torch.ops.aten.gelu_backward(x @ w.t(), aux, approximate="tanh").float().sum(0))
+            add("tcgen05 variant 3: (xW^T) * gelu'(aux)", lambda: linear_act(x, w, None, "dgelu", aux=aux, variant=3))
+            add("tcgen05 variant 3: dgelu + bias-grad column sums",
+                lambda: linear_act(x, w, None, "dgelu", aux=aux, colsum=cs, variant=3))
     res = {"shape": [a.m, a.n, a.k], "dtype": "bf16", "iters": a.iters,
            "l2": "working set per call (inputs + 1-2 outputs, 70-120 MB at the default shape) streams through L2",
            "rows": rows}

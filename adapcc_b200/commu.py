@@ -201,6 +201,8 @@ class CudaCommu:
         path = _arg(self.args, "strategy_file", None)
         if path and os.path.exists(path):
             self.strategy = Strategy.from_file(path, self.world_size)
+            from .synth.plan import AlgoPlan
+            self.plan = AlgoPlan.from_attrs(self.strategy.attrs)      # size bands written by the synthesizer
             if self.chunk_bytes is None and "chunk" in self.strategy.attrs:
                 try:
                     self.chunk_bytes = int(self.strategy.attrs["chunk"])
@@ -523,15 +525,37 @@ class CudaCommu:
             self.coordinator.set_traffic(self.coordinator.accumulated_size, self.accumulated_bw)
         ext = getattr(self, "_profile_ext", {"nvls": []})
         nvls = max(ext.get("nvls", [0.0]) or [0.0])
+        # ---- the per-message algorithm plan: every variant scored over the size axis with the PROFILED alpha / beta /
+        # NVLS bandwidth; the winners travel as size bands inside the strategy XML (all ranks execute the same
+        # decision) and as thresholds for the native runtime's own policy (synth/plan.py) -------------------------------
+        from .strategy.trees import Strategy as _Strategy
+        from .synth.plan import build_plan
+        path = _arg(self.args, "strategy_file", None)
+        strat = None
+        try:
+            strat = _Strategy.from_file(path, self.world_size) if path and os.path.exists(path) else None
+        except Exception as e:  # noqa: BLE001
+            self._log(f"plan: cannot re-read the synthesised strategy ({e})")
+        have_nvls = nvls > 0 or bool(self.native is not None and self.native.multicast)
+        plan = build_plan(self.link_model, strat, nvls=have_nvls, nvls_bw_gbs=nvls or None,
+                          ll=os.environ.get("ADAPCC_LL", "1") != "0")
+        if strat is not None:
+            strat.attrs.update(plan.to_attrs())
+            strat.save(path, compact=True)
         tun = {
             "one_shot_max_bytes": min(max(crossover_bytes(self.link_model, "one_shot", "two_shot", nvls=False), 16 << 10),
                                       4 << 20),
             "nvls_bw_gbs": nvls,
             "p2p_bw_gbs": self.link_model.min_bw(),
             "alpha_us": self.link_model.mean_alpha() * 1e6,
+            "bands": plan.to_attrs()["bands"], "bands_zc": plan.to_attrs()["bands_zc"],
         }
+        tun.update(plan.tunables())
+        if not self.link_model.is_uniform() or self.world_size <= 2:
+            tun["nvls_min_ranks"] = 3 if self.world_size > 2 else 99      # 2 ranks: a two-shot moves fewer bytes
         with open(self._tunables_path(), "w") as f:
             json.dump(tun, f, indent=1)
+        self._log(f"algorithm plan: staged [{tun['bands']}] zero-copy [{tun['bands_zc']}]")
 
     # ==========================================================================================
     # data plane
@@ -543,14 +567,28 @@ class CudaCommu:
             return self.wire_dtype
         return None
 
-    def _resolve_algo(self, numel, dtype, active) -> str:
-        """'tree' when the strategy must be honoured hop by hop (multi-server, or explicitly asked),
-        otherwise a direct algorithm picked per message by the native runtime."""
+    def _resolve_algo(self, numel, dtype, active, tensor=None, wire=None) -> str:
+        """The data-plane variant for this message. Explicit request (``args.algo``) first; then the strategy's own
+        ``algo=`` attribute; then the synthesizer's size bands (``bands`` / ``bands_zc`` of the strategy XML, built from
+        the profile: synth/plan.py) — 'tree' there means the synthesised trees are executed hop by hop; without a plan
+        the native runtime's threshold policy ('auto'). Multi-server strategies are always honoured as trees."""
         if self.algo != "auto":
             return self.algo
         if self.strategy is not None and self.strategy.attrs.get("algo") in ("tree", "one_shot", "two_shot", "nvls"):
             return self.strategy.attrs["algo"]
-        return "auto" if self.single_server else "tree"
+        if not self.single_server:
+            return "tree"
+        plan = getattr(self, "plan", None)
+        if plan is None:
+            return "auto"
+        import torch
+
+        esize = torch.empty((), dtype=getattr(torch, wire) if isinstance(wire, str) else dtype).element_size()
+        n = self.native
+        zero_copy = bool(tensor is not None and n is not None and wire is None and n.in_heap(tensor))
+        return plan.pick(int(numel) * esize, zero_copy=zero_copy, all_active=len(active) == self.world_size,
+                         nvls=bool(n is not None and n.multicast), ll=bool(n is not None and n.has_ll),
+                         tree=self.strategy is not None)
 
     def _collective(self, prim, buffer, size, chunk_bytes, active_gpus, op, root=None):
         import torch
@@ -574,8 +612,10 @@ class CudaCommu:
         if not self.single_server:
             self._hierarchical(n, prim, flat, active, op, root)
             return buffer
-        algo = self._resolve_algo(size, buffer.dtype, active)
         wire = self._wire_for(buffer.dtype)
+        algo = self._resolve_algo(size, buffer.dtype, active, tensor=flat, wire=wire)
+        if algo == "ll" and prim != ALLREDUCE:
+            algo = "auto"
         if self.nvtx:
             torch.cuda.nvtx.range_push(f"adapcc.prim{prim}.{algo}.{size * buffer.element_size()}B")
         try:

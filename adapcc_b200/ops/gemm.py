@@ -25,6 +25,7 @@ def _lib():
     lib = load_library()
     if not _bound:
         lib.adapcc_gemm_bias_act_v.argtypes = [c_void_p] * 5 + [c_int] * 5 + [c_void_p]
+        lib.adapcc_gemm_pp.argtypes = [c_void_p] * 6 + [c_int] * 4 + [c_void_p]
         _bound = True
     return lib
 
@@ -43,7 +44,8 @@ def default_variant() -> int:
 
 def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: str = "gelu",
                save_pre: bool = False, variant: Optional[int] = None,
-               aux: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+               aux: Optional[torch.Tensor] = None,
+               colsum: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """-> (result, pre-activation or None). x [..., K], weight [N, K], bias [N]; bf16.
 
     act "none" / "gelu": result = act(x @ weight.T + bias), optionally also the pre-activation (validated on B200).
@@ -59,6 +61,32 @@ def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     m = x2.shape[0]
     code = ACT[act]
     out = torch.empty(m, n, dtype=torch.bfloat16, device=x.device)
+    v_req = default_variant() if variant is None else int(variant)
+    if v_req == 3 and n % 256 == 0 and code <= 2:
+        # variant 3 (csrc/gemm_tcgen05_pp.cu): persistent CTA pairs, double-buffered TMEM, coalescing epilogue;
+        # act "dgelu" can also accumulate the column sums of its result (the up-projection's bias gradient)
+        if code == 2:
+            if aux is None or aux.numel() != m * n or aux.dtype != torch.bfloat16:
+                raise NativeError("linear_act(dgelu): aux must be a bf16 tensor with the result's shape")
+            pre = aux.reshape(m, n).contiguous()
+        else:
+            pre = torch.empty_like(out) if save_pre else None
+        if colsum is not None and (code != 2 or colsum.dtype != torch.float32 or colsum.numel() != n):
+            raise NativeError("linear_act: colsum is an fp32 [N] accumulator of the dgelu mode")
+        b = bias.contiguous() if bias is not None else None
+        rc = _lib().adapcc_gemm_pp(c_void_p(x2.data_ptr()), c_void_p(w.data_ptr()),
+                                   c_void_p(b.data_ptr() if b is not None else 0), c_void_p(out.data_ptr()),
+                                   c_void_p(pre.data_ptr() if pre is not None else 0),
+                                   c_void_p(colsum.data_ptr() if colsum is not None else 0), m, n, k, code,
+                                   c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise NativeError(f"gemm_pp failed: {last_error()}")
+        shape = x.shape[:-1] + (n,)
+        return out.view(shape), (pre.view(shape) if (pre is not None and code < 2) else None)
+    if colsum is not None:
+        raise NativeError("linear_act: colsum needs variant 3 (N % 256 == 0)")
+    if v_req == 3:
+        v_req = 1                                       # shapes variant 3 does not cover: the persistent 1-CTA kernel
     if code >= 2:
         if aux is None or aux.numel() != m * n or aux.dtype != torch.bfloat16:
             raise NativeError(f"linear_act({act}): aux must be a bf16 tensor with the result's shape")
@@ -66,7 +94,7 @@ def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
         v = 0                                           # only built for the per-tile variant
     else:
         pre = torch.empty_like(out) if save_pre else None
-        v = default_variant() if variant is None else int(variant)
+        v = v_req
     b = bias.contiguous() if bias is not None else None
     rc = _lib().adapcc_gemm_bias_act_v(c_void_p(x2.data_ptr()), c_void_p(w.data_ptr()),
                                        c_void_p(b.data_ptr() if b is not None else 0), c_void_p(out.data_ptr()),
@@ -119,8 +147,15 @@ class _MLPFn(torch.autograd.Function):
         dy = dy.contiguous()
         _, dw2, db2 = linear_backward(p2, h, w2, dy, needs_dx=False)
         # dH = dY . W2 needs W2 as a K-major [N = d_hidden, K = d_model] operand: one 4.7 MB transpose per layer
-        du, _ = linear_act(dy, w2.t().contiguous(), None, "dgelu", aux=pre)
-        dx, dw1, db1 = linear_backward(p1, x, w1, du, ctx.needs_input_grad[0])
+        w2t = w2.t().contiguous()
+        if default_variant() == 3 and w2t.shape[0] % 256 == 0:
+            # ... and the up-projection's bias gradient (column sums of dH) falls out of the same epilogue
+            db_acc = torch.zeros(w2t.shape[0], dtype=torch.float32, device=dy.device)
+            du, _ = linear_act(dy, w2t, None, "dgelu", aux=pre, colsum=db_acc, variant=3)
+            dx, dw1, db1 = linear_backward(p1, x, w1, du, ctx.needs_input_grad[0], db=db_acc)
+        else:
+            du, _ = linear_act(dy, w2t, None, "dgelu", aux=pre)
+            dx, dw1, db1 = linear_backward(p1, x, w1, du, ctx.needs_input_grad[0])
         return dx, dw1, db1, dw2, db2
 
 

@@ -180,9 +180,10 @@ class _LinearFn(torch.autograd.Function):
         return linear_backward(ctx.params, x, w, dy, ctx.needs_input_grad[0])
 
 
-def linear_backward(params, x, w, dy, needs_dx=True):
+def linear_backward(params, x, w, dy, needs_dx=True, db=None):
     """(dx, dw, db) of y = x @ w.T + b for bf16 CUDA tensors: two GEMMs + the column-sum kernel; dw / db
-    go straight into the parameters' flat-buffer gradient views when the engine's sinks are attached."""
+    go straight into the parameters' flat-buffer gradient views when the engine's sinks are attached.
+    ``db``: the bias gradient if the caller already has it (fp32 [N], e.g. accumulated in a GEMM epilogue)."""
     lib = _lib()
     n = w.shape[0]
     dy2 = dy.reshape(-1, n)
@@ -200,6 +201,12 @@ def linear_backward(params, x, w, dy, needs_dx=True):
         dw = dy2.t() @ x2
     rows = dy2.shape[0]
     direct_b = sb is not None and pb.grad.dtype == dy2.dtype and sb.begin()
+    if db is not None:                                # already reduced by the producer of dy
+        if direct_b:
+            pb.grad.copy_(db)
+            sb.done()
+            return dx, dw, None
+        return dx, dw, db.to(dy2.dtype)
     db = pb.grad if direct_b else torch.empty(n, dtype=dy2.dtype, device=dy2.device)
     part = torch.empty(lib.adapcc_colsum_splits(rows) * n, dtype=torch.float32, device=dy2.device)
     if lib.adapcc_colsum(_p(dy2), rows, n, _p(db), _p(part), _s()) != 0:

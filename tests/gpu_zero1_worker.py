@@ -17,12 +17,12 @@ from adapcc_b200.runtime.native import NativeComm  # noqa: E402
 from adapcc_b200.runtime.rendezvous import unique_name  # noqa: E402
 
 
-def run(comm, rank, world, dev, zero1, graph, steps=8):
+def run(comm, rank, world, dev, zero1, graph, steps=8, lr=2e-3):
     cfg = GPT2Config(vocab_size=1000, n_positions=64, n_embd=256, n_layer=2, n_head=4, lm_chunk_rows=128)
     torch.manual_seed(7)
     model = GPT2DoubleHeads(cfg).to(dev)
     comm.heap_reset()
-    eng = FlatDataParallel(model, comm, world_size=world, rank=rank, lr=2e-3, max_norm=1.0, bucket_mb=0.5,
+    eng = FlatDataParallel(model, comm, world_size=world, rank=rank, lr=lr, max_norm=1.0, bucket_mb=0.5,
                            zero1=zero1)
     assert eng.zero1 == zero1
     batches = [synthetic_batch(2, 2, 64, cfg.vocab_size, device=dev, seed=100 * rank + i) for i in range(3)]
@@ -48,19 +48,31 @@ def main():
     comm = NativeComm(unique_name("zero1"), rank, world, local, staging_bytes=16 << 20, heap_bytes=64 << 20)
     ok = True
     for graph in (False, True):
-        base_l, base_p = run(comm, rank, world, dev, zero1=False, graph=graph)
-        z_l, z_p = run(comm, rank, world, dev, zero1=True, graph=graph)
-        # every rank must hold the same parameters after the broadcast
+        # (1) ONE step from identical weights: the two modes compute the same update (same averaged gradients, same
+        # clip coefficient, same AdamW) on different ranks -> parameters agree except where a rounding-level gradient
+        # difference (fp32 atomics order in the embedding backward) flips Adam's first-step sign on a near-zero element
+        _, base_p = run(comm, rank, world, dev, zero1=False, graph=graph, steps=1)
+        _, z_p = run(comm, rank, world, dev, zero1=True, graph=graph, steps=1)
+        diff = (z_p - base_p).abs()
+        frac_off = float((diff > 2e-4).float().mean())
         ref = z_p.clone()
         dist.broadcast(ref, src=0)
         same = bool(torch.equal(ref, z_p))
-        drift = float((z_p - base_p).abs().max())
-        loss_gap = abs(z_l[-1] - base_l[-1]) / abs(base_l[-1])
-        good = same and loss_gap < 0.03 and base_l[-1] < base_l[0] - 0.1 and z_l[-1] < z_l[0] - 0.1
+        one_ok = same and frac_off < 2e-3
+        # (2) a short training run at a sane learning rate: both modes must learn, and to similar losses
+        base_l, _ = run(comm, rank, world, dev, zero1=False, graph=graph, steps=24, lr=5e-4)
+        z_l, z_p2 = run(comm, rank, world, dev, zero1=True, graph=graph, steps=24, lr=5e-4)
+        ref = z_p2.clone()
+        dist.broadcast(ref, src=0)
+        same2 = bool(torch.equal(ref, z_p2))
+        tail_b, tail_z = sum(base_l[-3:]) / 3, sum(z_l[-3:]) / 3
+        loss_gap = abs(tail_z - tail_b) / abs(tail_b)
+        good = one_ok and same2 and loss_gap < 0.08 and tail_b < base_l[0] - 0.1 and tail_z < z_l[0] - 0.1
         ok &= good
         if rank == 0 or not good:
-            print(f"[zero1] rank {rank} graph={graph}: baseline {base_l[0]:.3f}->{base_l[-1]:.3f}, "
-                  f"zero1 {z_l[0]:.3f}->{z_l[-1]:.3f}, replicas identical={same}, max param drift {drift:.3g} "
+            print(f"[zero1] rank {rank} graph={graph}: one step: replicas identical={same}, params differing by > 2e-4: "
+                  f"{frac_off:.2e} (max {float(diff.max()):.3g}, mean {float(diff.mean()):.3g}); 24 steps: baseline "
+                  f"{base_l[0]:.3f}->{tail_b:.3f}, zero1 {z_l[0]:.3f}->{tail_z:.3f}, replicas identical={same2} "
                   f"{'OK' if good else 'FAIL'}", flush=True)
     t = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(t)

@@ -7,12 +7,10 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-# variants 1 (persistent CTAs, double-buffered TMEM) and 2 (CTA pairs, cta_group::2) have been compiled and SASS-checked
-# but not run yet: a protocol bug would trap the kernel and poison this process's CUDA context, so they only run when
-# asked for, one process per variant: ADAPCC_EXPERIMENTAL=1 ADAPCC_TCGEN05_TEST_VARIANTS=1 (or 2, or 1,2)
-VARIANTS = [0]
-if os.environ.get("ADAPCC_EXPERIMENTAL", "0") == "1":
-    VARIANTS += [int(v) for v in os.environ.get("ADAPCC_TCGEN05_TEST_VARIANTS", "1,2").split(",") if v.strip()]
+# variants 0 (tile per CTA), 1 (persistent CTAs, double-buffered TMEM) and 2 (CTA pairs, cta_group::2) all passed on
+# B200 (round 2, gpurun call 1: gpurun_out/c1_tcgen05_v*.log); variant 3 (persistent pairs + coalescing epilogue,
+# csrc/gemm_tcgen05_pp.cu) is tested in tests/test_gpu_tcgen05_pp.py
+VARIANTS = [int(v) for v in os.environ.get("ADAPCC_TCGEN05_TEST_VARIANTS", "0,1,2").split(",") if v.strip()]
 
 
 @pytest.fixture(scope="module")
@@ -59,7 +57,6 @@ def test_linear_gelu_autograd_matches_torch(dev):
         assert err < 3e-2, err
 
 
-@pytest.mark.skipif(os.environ.get("ADAPCC_EXPERIMENTAL", "0") != "1", reason="aux epilogue modes: first GPU run pending")
 def test_aux_epilogues_and_fused_mlp(dev):
     from adapcc_b200.ops.gemm import linear_act, mlp_gelu
 

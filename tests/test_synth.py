@@ -165,3 +165,42 @@ def test_synth_cli_shape_and_measured_profile(tmp_path):
         out2 = tmp_path / "m.xml"
         assert main(["--profile-dir", prof, "--policy", "par-trees", "--out", str(out2)]) == 0
         Strategy.from_file(str(out2), 4).validate(4)
+
+
+def test_algorithm_plan_bands_follow_the_profile():
+    """The synthesizer scores every data-plane variant per message size from the profiled alpha / beta and writes the
+    winners as size bands into the strategy XML; a non-uniform profile (one slow link) flips the large-message band
+    from the switch algorithms — bounded by the slowest link every rank crosses — to the trees that route around it."""
+    from adapcc_b200.strategy import make_strategy
+    from adapcc_b200.synth.plan import INF_BYTES, AlgoPlan, build_plan
+    from adapcc_b200.synth.solver import Solver
+
+    world = 8
+    uniform = LinkModel.uniform(world, 2.0, 700.0)
+    s = make_strategy(world, 4, "binary")
+    plan = build_plan(uniform, s)
+    assert plan.pick(1 << 10) == "ll" and plan.pick(1 << 28, zero_copy=True) == "nvls"
+    assert plan.pick(1 << 28, zero_copy=False) in ("nvls", "two_shot")
+    assert all(a != "tree" for _, a in plan.bands + plan.bands_zc)            # never on a uniform switch
+    assert plan.bands[-1][0] == INF_BYTES and plan.bands_zc[-1][0] == INF_BYTES
+    # fall-backs: NVLS / LL need every rank; without them the next eligible band (or the native policy) is used
+    assert plan.pick(1 << 10, all_active=False) in ("one_shot", "two_shot", "auto")
+    assert plan.pick(1 << 28, zero_copy=True, nvls=False) == "auto"
+    # XML round trip
+    st = Strategy.from_xml(s.to_xml(), world)
+    st.attrs.update(plan.to_attrs())
+    again = AlgoPlan.from_attrs(Strategy.from_xml(st.to_xml(), world).attrs)
+    assert again.bands == plan.bands and again.bands_zc == plan.bands_zc
+    t = plan.tunables()
+    assert t["one_shot_max_bytes"] >= 1 << 16 and t["nvls_min_bytes"] <= 1 << 22
+    # one slow link (rank 0 <-> 1 at 20 GB/s): the MILP's trees avoid it, the switch algorithms cannot
+    bw = [[0.0 if i == j else 700.0 for j in range(world)] for i in range(world)]
+    bw[0][1] = bw[1][0] = 20.0
+    slow = LinkModel([[0.0 if i == j else 2.0 for j in range(world)] for i in range(world)], bw)
+    trees = Solver(time_limit_s=3.0).solve(4, float(1 << 28), bw, slow.alpha_us, ["h"] * world)
+    for t_ in trees.trees:
+        for x in t_.nodes:
+            assert {x, t_.parent.get(x, -1)} != {0, 1}, "a synthesised tree uses the slow link"
+    plan2 = build_plan(slow, trees)
+    assert plan2.pick(1 << 28, zero_copy=True) == "tree" and plan2.pick(1 << 28) == "tree"
+    assert plan2.pick(1 << 10) == "ll"

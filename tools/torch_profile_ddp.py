@@ -85,7 +85,10 @@ def main() -> int:
             ks.append((ev.time_range.start, ev.time_range.end, ev.name))
     ks.sort()
     # one `incr_int_kernel` per step marks the start of the optimizer; the optimizer's own kernels follow it
-    OPT_PAT = re.compile(r"sumsq_kernel|adamw|barrier|allreduce_direct_kernel|allreduce_ll_kernel|skip_op|Memset|ncclDevKernel")
+    OPT_PAT = re.compile(r"sumsq_kernel|adamw|barrier|allreduce_direct_kernel|allreduce_ll_kernel|skip_op|ncclDevKernel")
+
+    def in_optimizer(k):            # tiny fills / memsets (sumsq.zero_()) belong to it; the 249 MB gradient clear does not
+        return bool(OPT_PAT.search(k[2])) or ((k[1] - k[0]) < 5.0 and re.search(r"Fill|Memset|elementwise", k[2]) is not None)
     starts = [i for i, k in enumerate(ks) if "incr_int_kernel" in k[2]]
     lines = []
     bucket_elems = [b.end - b.start for b in eng.buckets]
@@ -95,7 +98,7 @@ def main() -> int:
     summary = []
     for si, opt_i in enumerate(starts):
         last = opt_i
-        while last + 1 < len(ks) and OPT_PAT.search(ks[last + 1][2]):
+        while last + 1 < len(ks) and in_optimizer(ks[last + 1]):
             last += 1
         seg = ks[step_begin:last + 1]
         step_begin = last + 1
