@@ -44,7 +44,7 @@ def main():
     from ..adapcc import AdapCC
 
     args = SimpleNamespace(port=5000, strategy_file="./strategy/wait.xml", logical_graph="./topology/lg.xml",
-                           entry_point=-1, parallel_degree=4, profile_freq=0, relay_control=True,
+                           entry_point=-1, parallel_degree=4, profile_freq=0, relay_control=True, coordinator_process=False,
                            relay_threshold=10.0,                      # never exclude anybody: we only measure
                            backend="nccl" if cuda else "gloo")
     AdapCC.init(args, local, rank, world)

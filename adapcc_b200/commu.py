@@ -108,13 +108,27 @@ class CudaCommu:
         self.coordinator_port = int(_arg(args, "coordinator_port", os.environ.get("ADAPCC_COORD_PORT", 50051)))
         self.controller: Optional[Controller] = None
         self.hooker: Optional[Hooker] = None
+        self._coord_proc = None
         if self.relay_control:
             if world_rank == 0:
-                self.coordinator = Coordinator(self.ip_table[0], self.coordinator_port, world_size,
-                                               relay_threshold=float(_arg(args, "relay_threshold", 0.1)),
-                                               fault_tolerant_time=float(_arg(args, "fault_tolerant_time", 10.0)))
-                self.server = make_server(self.coordinator)
-                self.server.start()
+                # The coordinator answers two blocking RPCs per rank per step. Hosted as a THREAD of rank 0 (the
+                # reference's layout, /root/reference/commu.py:80-84) its handlers compete for rank 0's GIL with a
+                # launch-bound training loop: one hand-off per 5 ms switch interval -> 16 ms per negotiation on 8
+                # ranks (profiles/straggler_8xB200.json) against a 9 ms step. Default on CUDA jobs: a separate
+                # PROCESS (same module, same protocol); `coordinator_process=False` keeps the in-process object
+                # (tests and tools that read `communicator.coordinator` directly).
+                as_process = bool(_arg(args, "coordinator_process",
+                                       os.environ.get("ADAPCC_COORD_PROCESS", "1" if self._use_cuda() else "0") == "1"))
+                if as_process and world_size > 1:
+                    self._spawn_coordinator(args, world_size)
+                if self._coord_proc is None:
+                    self.coordinator = Coordinator(self.ip_table[0], self.coordinator_port, world_size,
+                                                   relay_threshold=float(_arg(args, "relay_threshold", 0.1)),
+                                                   fault_tolerant_time=float(_arg(args, "fault_tolerant_time", 10.0)))
+                    self.server = make_server(self.coordinator)
+                    self.server.start()
+                    import sys as _sys
+                    _sys.setswitchinterval(min(_sys.getswitchinterval(), 0.0005))   # faster GIL hand-off to the handlers
             rpc_timeout = float(_arg(args, "fault_tolerant_time", 10.0)) * 2 + float(_arg(args, "relay_threshold", 0.1)) + 20
             self.controller = Controller(self.ip_table[0], self.coordinator_port, timeout=rpc_timeout)
             self.hooker = Hooker(self.ip_table[0], self.coordinator_port, timeout=rpc_timeout)
@@ -150,6 +164,29 @@ class CudaCommu:
             dist.barrier()
         elif self.native is not None:
             self.native.host_barrier()
+
+    def _spawn_coordinator(self, args, world_size: int) -> None:
+        import subprocess
+        import sys as _sys
+
+        cmd = [_sys.executable, "-m", "adapcc_b200.coord.server", "--ip", str(self.ip_table[0]),
+               "--port", str(self.coordinator_port), "--world_size", str(world_size),
+               "--relay_threshold", str(float(_arg(args, "relay_threshold", 0.1))),
+               "--fault_tolerant_time", str(float(_arg(args, "fault_tolerant_time", 10.0))),
+               "--parent", str(os.getpid())]
+        env = dict(os.environ)
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+        env["CUDA_VISIBLE_DEVICES"] = ""                    # the coordinator never touches a GPU
+        try:
+            proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env)
+            line = proc.stdout.readline()                   # "coordinator ready" once the port is bound
+            if "ready" in line and proc.poll() is None:
+                self._coord_proc = proc
+                return
+            proc.kill()
+        except OSError as e:
+            self._log(f"coordinator process could not start ({e}); hosting it in-process")
 
     def _use_cuda(self) -> bool:
         import torch
@@ -191,7 +228,7 @@ class CudaCommu:
         try:
             with open(self._tunables_path()) as f:
                 t = json.load(f)
-            for k in ("one_shot_max_bytes", "nvls_min_bytes", "max_blocks", "tree_blocks", "nvls_min_ranks"):
+            for k in ("one_shot_max_bytes", "nvls_min_bytes", "max_blocks", "tree_blocks", "nvls_min_ranks", "ll_max_bytes"):
                 if k in t:
                     self.native.set_tunable(k, int(t[k]))
         except (OSError, ValueError) as e:
@@ -305,6 +342,13 @@ class CudaCommu:
         if self.server is not None:
             self.server.stop(1)
             self.server = None
+        if getattr(self, "_coord_proc", None) is not None:
+            self._coord_proc.terminate()
+            try:
+                self._coord_proc.wait(timeout=3)
+            except Exception:  # noqa: BLE001
+                self._coord_proc.kill()
+            self._coord_proc = None
         kept = None
         if self.native is not None:
             self._barrier()
@@ -538,7 +582,7 @@ class CudaCommu:
             self._log(f"plan: cannot re-read the synthesised strategy ({e})")
         have_nvls = nvls > 0 or bool(self.native is not None and self.native.multicast)
         plan = build_plan(self.link_model, strat, nvls=have_nvls, nvls_bw_gbs=nvls or None,
-                          ll=os.environ.get("ADAPCC_LL", "1") != "0")
+                          ll=os.environ.get("ADAPCC_LL", "1") != "0" and self.world_size > 1)
         if strat is not None:
             strat.attrs.update(plan.to_attrs())
             strat.save(path, compact=True)

@@ -197,7 +197,27 @@ if __name__ == "__main__":
     ap.add_argument("--ip", default="127.0.0.1")
     ap.add_argument("--port", type=int, default=50051)
     ap.add_argument("--world_size", type=int, default=4)
+    ap.add_argument("--relay_threshold", type=float, default=0.1)
+    ap.add_argument("--time_slot_duration", type=float, default=0.005)
+    ap.add_argument("--fault_tolerant_time", type=float, default=10.0)
+    ap.add_argument("--accumulated_size", type=float, default=100 * 8 / 1024)
+    ap.add_argument("--accumulated_bandwidth", type=float, default=0.0)
+    ap.add_argument("--parent", type=int, default=0, help="exit when this process disappears (the rank that spawned us)")
     a = ap.parse_args()
-    srv = make_server(Coordinator(a.ip, a.port, a.world_size))
+    srv = make_server(Coordinator(a.ip, a.port, a.world_size, relay_threshold=a.relay_threshold,
+                                  time_slot_duration=a.time_slot_duration, fault_tolerant_time=a.fault_tolerant_time,
+                                  accumulated_size=a.accumulated_size,
+                                  accumulated_bandwidth=a.accumulated_bandwidth or None))
     srv.start()
-    srv.wait_for_termination()
+    print("coordinator ready", flush=True)
+    if a.parent:
+        import os
+
+        while srv.wait_for_termination(timeout=1.0):        # True = timed out, still serving
+            try:
+                os.kill(a.parent, 0)
+            except OSError:
+                break                                       # orphaned: the training job is gone
+        srv.stop(0)
+    else:
+        srv.wait_for_termination()

@@ -86,6 +86,7 @@ int adapcc_ctx_set_tunable(void* h, int key, long long value) {
     case 11: c->tun.pipe_links = (int)value; break;
     case 12: c->tun.pipe_piece_bytes = value; break;
     case 13: c->tun.pipe_nvls = (int)value; break;
+    case 14: c->tun.ll_max_bytes = value; break;
     default: set_error("unknown tunable %d", key); return -1;
   }
   return 0;

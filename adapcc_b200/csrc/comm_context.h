@@ -18,6 +18,7 @@ struct Tunables {
   int max_blocks = 64;                 // CTAs per collective kernel (same on all ranks)
   long long one_shot_max_bytes = 256 << 10;   // wire bytes: <= -> one-shot
   long long nvls_min_bytes = 0;        // wire bytes: >= -> NVLS when available
+  long long ll_max_bytes = 32768;      // AUTO: all-rank messages up to this size use the LL kernel (0 = never)
   int nvls_min_ranks = 3;              // NVLS only pays off when >2 ranks share the switch reduction
   int relay_mode = RELAY_FORWARD;
   long long timeout_ms = 30000;
@@ -61,7 +62,7 @@ class CommContext {
   int tree_relay_persistent(int n_buckets, const long long* counts, const long long* chunk_bytes, int wire, int op,
                             const std::vector<int>& active, cudaStream_t stream);
   // Low-latency one-shot all-reduce (kernels_ll.cuh): all ranks active, <= 32 KB, flag-in-data, no barrier.
-  // Only available when the context was created with ADAPCC_LL=1 (allocates the 2 MB LL buffer).
+  // Available unless the context was created with ADAPCC_LL=0 (the 2 MB LL buffer is allocated by default).
   int allreduce_ll(const void* in, void* out, long long count, int dtype, int op, cudaStream_t stream);
   bool has_ll() const { return ll_.size != 0; }
   int skip_op(cudaStream_t stream);

@@ -342,13 +342,13 @@ gemm_pair_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             st_shared_v4(my_row + (uint32_t)h * 64 + (uint32_t)v * 16, make_uint4(po[4 * v], po[4 * v + 1], po[4 * v + 2], po[4 * v + 3]));
-            if (ACT == 1 && pre != nullptr)
+            if (ACT <= 1 && pre != nullptr)
               st_shared_v4(my_row_aux + (uint32_t)h * 64 + (uint32_t)v * 16, make_uint4(pp[4 * v], pp[4 * v + 1], pp[4 * v + 2], pp[4 * v + 3]));
           }
         }
         __syncwarp();
         chunk_to_global(st_out, out + col0, (size_t)N, row0, rows_valid, lane);
-        if (ACT == 1 && pre != nullptr) chunk_to_global(st_aux, pre + col0, (size_t)N, row0, rows_valid, lane);
+        if (ACT <= 1 && pre != nullptr) chunk_to_global(st_aux, pre + col0, (size_t)N, row0, rows_valid, lane);
         if (ACT == 2 && colsum != nullptr) {
           // bias gradient: lane l sums columns 2l, 2l+1 of the staged bf16 chunk over the valid rows
           float s0 = 0.f, s1 = 0.f;
@@ -432,7 +432,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const void* bias
 
 using namespace adapcc;
 
-// act 0 / 1: out = act(a @ w^T + bias), pre (optional output, act 1) = a @ w^T + bias.
+// act 0 / 1: out = act(a @ w^T + bias), pre (optional output) = a @ w^T + bias.
 // act 2: out = (a @ w^T) * gelu'(pre)  (pre = aux INPUT), colsum (optional, fp32 [N], accumulated into) += column sums.
 // bf16 row-major operands, 16-byte aligned; K % 64 == 0, N % 256 == 0.
 extern "C" int adapcc_gemm_pp(const void* a, const void* w, const void* bias, void* out, void* pre, float* colsum,

@@ -87,6 +87,7 @@ class AlgoPlan:
             prev = mx
         if "one_shot_max_bytes" not in t:
             t["one_shot_max_bytes"] = 0
+        t["ll_max_bytes"] = max([mx for mx, a in self.bands if a == "ll"] + [0])
         if not any(a == "nvls" for _, a in self.bands + self.bands_zc):
             t["nvls_min_bytes"] = INF_BYTES            # never
         return t

@@ -45,12 +45,12 @@ def main():
     ddp = wrap_ddp(model, AdapCC.communicator, local, zero_copy=False)
     opt = torch.optim.SGD(ddp.parameters(), lr=1e-3)
     for i in range(a.steps):
-        AdapCC.communicator.update_relay(step=i)
         if i and AdapCC.profile_freq and i % AdapCC.profile_freq == 0:
             t0 = time.time()
             AdapCC.reconstruct_topology(a, ALLREDUCE)     # re-profile links, re-synthesise, new contexts
             if rank == 0:
                 print("reconstruct_topology: %.1f ms" % ((time.time() - t0) * 1e3), flush=True)
+        AdapCC.communicator.update_relay(step=i)          # after the reconstruct: heartbeat goes to the LIVE coordinator
         t0 = time.time()
         x = torch.randn(a.batch, 3, cfg.image_size, cfg.image_size, device=dev, dtype=torch.bfloat16)
         y = torch.randint(0, cfg.num_classes, (a.batch,), device=dev)

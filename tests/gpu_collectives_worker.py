@@ -97,8 +97,8 @@ def main():
                     comm.check()
                     want = ref_reduce(world, n, dtype, seed, op, all_ranks, wire_t)
                     check(f"allreduce {algo} {dtype} wire={wire} {op} n={n}", x, want, dtype, wire_t, world)
-    # ---- reduce-scatter = reduce with root = self (opt-in until its first GPU run) ---------------------
-    if os.environ.get("ADAPCC_EXPERIMENTAL", "0") == "1":
+    # ---- reduce-scatter = reduce with root = self, all-gather = one direct broadcast per shard -------------
+    if True:
         for dtype in (torch.float32, torch.bfloat16):
             for algo in algos:
                 if algo == "one_shot":
@@ -122,7 +122,7 @@ def main():
                         comm.check()
                         check(f"all_gather after reduce_scatter {algo} {dtype} n={n} zc={zc}", x, want, dtype, None,
                               world)
-    # ---- opt-in low-latency path (ADAPCC_LL=1 in the environment of every rank) --------------------
+    # ---- low-latency path (flag-in-data; default on, ADAPCC_LL=0 turns the buffer off) --------------------
     if comm.has_ll:
         for dtype in (torch.float32, torch.bfloat16, torch.float16):
             for op in ("sum", "avg", "max"):
@@ -296,7 +296,7 @@ def main():
         "chain2": "<trees>" + "".join(chain_xml(o) for o in orders[:2]) + "</trees>",
         "binary": "<trees>" + "".join(bin_xml(o) for o in orders) + "</trees>",
     }
-    if os.environ.get("ADAPCC_EXPERIMENTAL", "0") == "1":
+    if True:
         # random spanning trees (arbitrary fan-out and depth), the shapes the CPU property test covers
         import random as _random
 

@@ -118,6 +118,23 @@ def main() -> int:
             nm = re.sub(r"^void\s+|adapcc::", "", k[2])[:70]
             lines.append(f"| {nm} | {(k[0] - t0) / 1e3:.3f} | {(k[1] - k[0]):.1f} | {'yes' if ov else 'NO (exposed)'} |\n")
         lines.append("\n")
+        if si == len(starts) - 1:
+            # the last 24 kernels before the optimizer (what the step's tail is made of) ...
+            before = [k for k in seg if k[0] < sumsq_start][-24:]
+            lines.append("last kernels before the optimizer (start ms, us, name):\n\n```\n")
+            for k in before:
+                lines.append(f"{(k[0] - t0) / 1e3:8.3f} {(k[1] - k[0]):8.1f}  {re.sub(r'^void |adapcc::', '', k[2])[:100]}\n")
+            lines.append("```\n\n")
+            # ... and the step's compute kernels by name, to diff against another world size
+            by = {}
+            for k in comp_k:
+                nm = re.sub(r"<.*", "", re.sub(r"^void\s+", "", k[2])).replace("at::native::", "native::")[:80]
+                c, t = by.get(nm, (0, 0.0))
+                by[nm] = (c + 1, t + (k[1] - k[0]))
+            lines.append("| compute kernel (this step) | launches | us |\n|---|---|---|\n")
+            for nm, (c, t) in sorted(by.items(), key=lambda kv: -kv[1][1])[:40]:
+                lines.append(f"| {nm} | {c} | {t:.1f} |\n")
+            lines.append("\n")
         summary.append(((seg[-1][1] - t0) / 1e3, comp_time / 1e3, (sumsq_start - bwd_end) / 1e3,
                         sum(k[1] - k[0] for k in comm_k) / 1e3))
     if summary:
