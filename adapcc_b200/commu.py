@@ -267,10 +267,15 @@ class CudaCommu:
                 self._log(f"controller RPC failed: {e}")
                 return
             if status == 0:
-                self.fault_worker_list = [w for w in range(self.world_size) if w not in active]
+                # heartbeat deadline missed by somebody: the survivors ARE the new world. The reference prints and lets
+                # the controller thread die (/root/reference/commu.py:151-157); here the thread keeps serving, the
+                # active set is re-formed from the survivors and the coordinator stops waiting for the dead ranks.
+                self.fault_worker_list = sorted(set(self.fault_worker_list) |
+                                                {w for w in range(self.world_size) if w not in active})
                 print(f"Fault occurs: rank {self.world_rank} alive; missing {self.fault_worker_list}", flush=True)
+                self.active_gpus = sorted(a for a in active if a not in self.fault_worker_list)
                 self.bsp_queue.put(step)
-                return
+                continue
             self.active_gpus = sorted(active)
             self._log(f"Controller active: {active}")
             if step <= 1:

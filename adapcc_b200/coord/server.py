@@ -54,6 +54,7 @@ class Coordinator:
         self._lock = threading.Lock()
         self._cv = threading.Condition(self._lock)
         self._steps: Dict[int, _Step] = {}
+        self.dead: set = set()       # ranks declared failed (missed a heartbeat deadline): never waited for again
         self.arrival_log: Dict[int, List[Tuple[int, float]]] = {}   # straggler-gap measurement hook
 
     # -- cost model -----------------------------------------------------------------------
@@ -75,8 +76,11 @@ class Coordinator:
         co_m = (num_ready - 1) / num_ready
         return self.rent0() * (co_m / co_n) + n * self.accumulated_size / self.accumulated_bandwidth
 
+    def alive_count(self) -> int:
+        return self.world_size - len(self.dead)
+
     def should_stop(self, waited: float, num_ready: int) -> bool:
-        if num_ready >= self.world_size:
+        if num_ready >= self.alive_count():
             return True
         if num_ready <= 1:
             return False
@@ -131,10 +135,14 @@ class Coordinator:
                 st.heartbeats.append(world_rank)
             self._cv.notify_all()
             deadline = time.time() + self.fault_tolerant_time
-            while len(st.heartbeats) < self.world_size:
+            while len([h for h in st.heartbeats if h not in self.dead]) < self.alive_count():
                 left = deadline - time.time()
                 if left <= 0:
-                    return list(st.heartbeats), 0           # fault: report the survivors
+                    # fault: the ranks that did not report are dead from now on — later steps expect only the
+                    # survivors (the reference re-runs the 10 s timeout every step, /root/reference/proto/rpc_server.py:48-59)
+                    self.dead |= {r for r in range(self.world_size) if r not in st.heartbeats}
+                    self._cv.notify_all()
+                    return list(st.heartbeats), 0           # report the survivors
                 self._cv.wait(timeout=min(left, 0.05))
             deadline = time.time() + self.fault_tolerant_time + self.relay_threshold
             while not st.decided:

@@ -144,8 +144,13 @@ void CommContext::destroy() {
   d_state_ = nullptr;
   if (d_pipe_) cudaFree(d_pipe_);
   d_pipe_ = nullptr;
-  if (d_relay_work_) cudaFree(d_relay_work_);
-  d_relay_work_ = nullptr;
+  for (int i = 0; i < 2; ++i) {
+    if (d_relay_work_[i]) cudaFree(d_relay_work_[i]);
+    if (h_relay_work_[i]) cudaFreeHost(h_relay_work_[i]);
+    if (relay_ev_[i]) cudaEventDestroy(relay_ev_[i]);
+    d_relay_work_[i] = h_relay_work_[i] = nullptr;
+    relay_ev_[i] = nullptr;
+  }
   relay_work_cap_ = 0;
   symm_.destroy();
 }
@@ -475,17 +480,28 @@ int CommContext::tree_collective(int prim, const void* in, void* out, long long 
   const float scale = (op == AVG && n_contrib > 0) ? 1.f / (float)n_contrib : 1.f;
   const int kop = (op == MAX) ? MAX : SUM;
 
-  Window w{};
-  for (int r = 0; r < world_; ++r) w.data[r] = (char*)staging_.peers[r];
-  w.mc = (char*)staging_.mc;
-  w.capacity = staging_.size;
-  w.zero_copy = false;
+  // Tensors inside the symmetric heap are reduced IN PLACE (no staging pass in either direction): a rank's chunk region
+  // goes own data -> partial sum (pulled by its parent) -> final result (pulled from its parent), and the flag chain
+  // orders every overwrite after the last read of the previous content. Needs every rank active (a relay has no tensor
+  // at that offset) and a whole number of 16-byte packs.
+  Window w = resolve(in, out, (size_t)count * esize, dtype == wire);
+  // (REDUCE keeps the staged path: in place it would leave partial sums in the non-root ranks' tensors)
+  const bool zc = w.zero_copy && prim != REDUCE && (int)active.size() == world_ && (((size_t)count * esize) & 15) == 0 &&
+                  in != nullptr;
+  if (!zc) {
+    w = Window{};
+    for (int r = 0; r < world_; ++r) w.data[r] = (char*)staging_.peers[r];
+    w.mc = (char*)staging_.mc;
+    w.capacity = staging_.size;
+    w.zero_copy = false;
+  }
   DevComm dc;
   if (fill_comm(participants, w, &dc)) return -1;
 
   TreePlan plan;
   memset(&plan, 0, sizeof(plan));
   plan.n_trees = nt;
+  plan.zero_copy = zc ? 1 : 0;
   plan.do_reduce = prim != BOARDCAST;
   plan.do_bcast = prim != REDUCE;
   // the API's chunk size is an upper bound; the device pipelines at a finer granularity so
@@ -501,7 +517,7 @@ int CommContext::tree_collective(int prim, const void* in, void* out, long long 
     if (tr.n_children > kMaxChildren) { set_error("too many children in tree %d", t); return -1; }
     for (int i = 0; i < tr.n_children; ++i) tr.children[i] = mine[t].children[i];
   }
-  const long long cap_elems = (long long)(w.capacity / 16) * epp;
+  const long long cap_elems = zc ? count : (long long)(w.capacity / 16) * epp;
   long long done = 0;
   while (done < count) {
     const long long n = std::min(count - done, cap_elems);
@@ -614,13 +630,24 @@ int CommContext::tree_relay_persistent(int n_buckets, const long long* counts, c
   }
   const size_t bytes = sizeof(RelayWork) * works.size();
   if (bytes > relay_work_cap_) {
-    if (d_relay_work_) cudaFree(d_relay_work_);
-    CUDA_TRY(cudaMalloc(&d_relay_work_, bytes));
+    CUDA_TRY(cudaStreamSynchronize(stream));            // (re)allocation only: first step / more buckets than before
+    for (int i = 0; i < 2; ++i) {
+      if (d_relay_work_[i]) cudaFree(d_relay_work_[i]);
+      if (h_relay_work_[i]) cudaFreeHost(h_relay_work_[i]);
+      CUDA_TRY(cudaMalloc(&d_relay_work_[i], bytes));
+      CUDA_TRY(cudaMallocHost(&h_relay_work_[i], bytes));
+      if (!relay_ev_[i]) CUDA_TRY(cudaEventCreateWithFlags(&relay_ev_[i], cudaEventDisableTiming));
+    }
     relay_work_cap_ = bytes;
   }
-  // synchronous copy: the descriptor vector lives on this stack frame
-  CUDA_TRY(cudaStreamSynchronize(stream));
-  CUDA_TRY(cudaMemcpy(d_relay_work_, works.data(), bytes, cudaMemcpyHostToDevice));
+  // asynchronous upload through a pinned slot; a slot is rewritten only after the copy issued from it two steps ago
+  // has executed (the event wait is a no-op in steady state) — no stream synchronisation on the relay path
+  const int slot = relay_slot_;
+  relay_slot_ ^= 1;
+  CUDA_TRY(cudaEventSynchronize(relay_ev_[slot]));
+  memcpy(h_relay_work_[slot], works.data(), bytes);
+  CUDA_TRY(cudaMemcpyAsync(d_relay_work_[slot], h_relay_work_[slot], bytes, cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaEventRecord(relay_ev_[slot], stream));
   Window win{};
   for (int r = 0; r < world_; ++r) win.data[r] = (char*)staging_.peers[r];
   win.mc = (char*)staging_.mc;
@@ -629,7 +656,7 @@ int CommContext::tree_relay_persistent(int n_buckets, const long long* counts, c
   if (fill_comm(participants, win, &dc)) return -1;
   const int kop = (op == MAX) ? MAX : SUM;
   const int blocks = 2 * max_lanes;
-  const RelayWork* dw = static_cast<const RelayWork*>(d_relay_work_);
+  const RelayWork* dw = static_cast<const RelayWork*>(d_relay_work_[slot]);
 #define RELAY_LAUNCH(W_)                                                                              \
   do {                                                                                                \
     if (kop == MAX) tree_relay_persistent_kernel<W_, MAX><<<blocks, kThreads, 0, stream>>>(dc, dw, n_buckets); \

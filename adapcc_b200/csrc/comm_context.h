@@ -102,8 +102,11 @@ class CommContext {
   SymmBuffer staging_, heap_, sig_, ll_;
   char* d_state_ = nullptr;            // bar_epoch[], ticket, err, seq
   void* d_pipe_ = nullptr;             // PipeState of the pipelined staged kernel
-  void* d_relay_work_ = nullptr;       // RelayWork[] scratch of the persistent relay kernel
+  void* d_relay_work_[2] = {nullptr, nullptr};   // RelayWork[] of the persistent relay kernel, double-buffered:
+  void* h_relay_work_[2] = {nullptr, nullptr};   // pinned host copies + one event per slot, so a step's descriptors are
+  cudaEvent_t relay_ev_[2] = {nullptr, nullptr}; // uploaded asynchronously (no stream sync on the relay path)
   size_t relay_work_cap_ = 0;
+  int relay_slot_ = 0;
   Strategy strategy_;
   int rank_ = 0, world_ = 1, device_ = 0;
   bool inited_ = false;

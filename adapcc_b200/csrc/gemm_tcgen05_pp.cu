@@ -41,7 +41,8 @@ constexpr uint32_t kABytes = 128 * kBK * 2, kBBytes = 128 * kBK * 2, kStageBytes
 constexpr uint32_t kRowPitch = 144;             // staging row: 64 bf16 (128 B) + 16 B pad -> conflict-free both ways
 constexpr uint32_t kStageTile = 32 * kRowPitch; // one warp's 32 x 64 chunk
 constexpr uint32_t kEpiBytes = kEpiWarps * 2 * kStageTile;
-constexpr uint32_t kBarOffset = kStages * kStageBytes + kEpiBytes;
+constexpr uint32_t kBiasBytes = kEpiWarps * 128 * 4;            // each epilogue warp's 128 bias values of the tile, as fp32
+constexpr uint32_t kBarOffset = kStages * kStageBytes + kEpiBytes + kBiasBytes;
 // full[S] empty[S] acc_full[2] acc_empty[2] + tmem slot
 constexpr uint32_t kSmemTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
 constexpr uint32_t kSmemDynamic = kSmemTotal + 1024;
@@ -58,7 +59,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      // default (acquire.cta) semantics on purpose: a cluster-scope acquire makes ptxas emit CCTL.IVALL (an L1
+      // invalidate) after EVERY successful wait — 17 % of all stall samples in the first ncu capture of this kernel, most
+      // of them in the MMA issuer's per-slab wait (tensor pipe 50 % busy). Nothing read after these waits needs it: the
+      // operands arrive through the async proxy (complete_tx), and acc_empty only orders TMEM reuse.
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
@@ -79,7 +84,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {      
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t cta) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(cta));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  // relaxed: the only thing ordered by this arrive is "my tcgen05.ld of the accumulator have completed", which
+  // tcgen05.wait::ld + fence::before_thread_sync already guarantee; a release would also drain the tile's global stores
+  // (ncu: 12 % of the epilogue's issue slots stalled on membar)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -285,12 +293,26 @@ gemm_pair_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
     const int e = warp - 2, q = warp & 3, half = e >> 2;
     const uint32_t st_out = base + kStages * kStageBytes + (uint32_t)e * 2 * kStageTile, st_aux = st_out + kStageTile;
     const uint32_t my_row = st_out + (uint32_t)lane * kRowPitch, my_row_aux = st_aux + (uint32_t)lane * kRowPitch;
+    const uint32_t st_bias = base + kStages * kStageBytes + kEpiBytes + (uint32_t)e * 512;
     uint32_t local = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
       const uint32_t as = local & 1u, use = local >> 1;
       const int row0 = m_blk * kTileM + (int)cta * 128 + q * 32;    // this warp's 32 rows; lane = row
       const int rows_valid = min(32, M - row0);
+      if (ACT != 2) {
+        // this warp's 128 bias values of the tile -> fp32 in shared memory once (every lane needs all of them for its
+        // row: broadcast LDS.128 below instead of 16-byte global loads + bf16 unpacking per 32 columns)
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias != nullptr) {
+          const uint2 t = __ldg(reinterpret_cast<const uint2*>(bias + n_blk * kTileN + half * 128 + lane * 4));
+          const float2 lo = unpack_bf16x2(t.x), hi = unpack_bf16x2(t.y);
+          bv = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_bias + (uint32_t)lane * 16), "f"(bv.x), "f"(bv.y),
+                     "f"(bv.z), "f"(bv.w) : "memory");
+        __syncwarp();
+      }
       mbar_wait(acc_full(as), use & 1u);
       tc_fence_after();
 #pragma unroll 1
@@ -319,23 +341,22 @@ gemm_pair_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
               }
             }
           } else {
-            const uint4* bp = reinterpret_cast<const uint4*>(bias + col0 + h * 32);
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              uint4 t = make_uint4(0u, 0u, 0u, 0u);
-              if (bias != nullptr) t = __ldg(bp + v);
-              const uint32_t bw[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 b2 = unpack_bf16x2(bw[j]);
-                const int i = v * 4 + j;
-                pp[i] = pack_bf16x2(__uint_as_float(acc[2 * i]) + b2.x, __uint_as_float(acc[2 * i + 1]) + b2.y);
-                if (ACT == 1) {                   // the activation sees the bf16-rounded pre-activation (like torch)
-                  const float2 r = unpack_bf16x2(pp[i]);
-                  po[i] = pack_bf16x2(gelu_tanh(r.x), gelu_tanh(r.y));
-                } else {
-                  po[i] = pp[i];
-                }
+            for (int v = 0; v < 8; ++v) {
+              float4 b4;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
+                           : "r"(st_bias + (uint32_t)(cc * 64 + h * 32 + v * 4) * 4) : "memory");
+              const float r0 = __uint_as_float(acc[4 * v]) + b4.x, r1 = __uint_as_float(acc[4 * v + 1]) + b4.y;
+              const float r2 = __uint_as_float(acc[4 * v + 2]) + b4.z, r3 = __uint_as_float(acc[4 * v + 3]) + b4.w;
+              pp[2 * v] = pack_bf16x2(r0, r1);
+              pp[2 * v + 1] = pack_bf16x2(r2, r3);
+              if (ACT == 1) {       // GELU on the fp32 pre-activation (torch applies it to the bf16-rounded one: the two
+                                    // differ by less than the output's own bf16 rounding)
+                po[2 * v] = pack_bf16x2(gelu_tanh(r0), gelu_tanh(r1));
+                po[2 * v + 1] = pack_bf16x2(gelu_tanh(r2), gelu_tanh(r3));
+              } else {
+                po[2 * v] = pp[2 * v];
+                po[2 * v + 1] = pp[2 * v + 1];
               }
             }
           }

@@ -28,6 +28,7 @@ struct TreeRole {
 struct TreePlan {
   int n_trees;
   int do_reduce, do_bcast;
+  int zero_copy;                 // the tensors live at the same heap offset on every rank: reduce / broadcast in place
   long long chunk_packs;
   long long slice_begin[kMaxTrees + 1];   // in packs; slice t = [begin[t], begin[t+1])
   TreeRole role[kMaxTrees];
@@ -154,15 +155,16 @@ __device__ __forceinline__ void tree_collective_body(const DevComm& c, const Tre
           __syncthreads();
         }
         const bool has_local = role.flags & TR_HAS_LOCAL;
-        const bool to_user = is_root && (role.flags & TR_WANT_RESULT);
         const bool to_window = !is_root || (plan.do_bcast && (role.flags & TR_PUBLISH));
+        // in place the window IS the user tensor: one store
+        const bool to_user = is_root && (role.flags & TR_WANT_RESULT) && !(plan.zero_copy && to_window);
         reduce_chunk<U, W, OP, 2, 4>(c, role, p0, pc, in, out, n, in_vec, out_vec, local, has_local, is_root,
                                      to_window, to_user, scale);
         __syncthreads();
         if (threadIdx.x == 0) st_release_sys64(is_root ? my_root_bflag : my_rflag, token);
       } else if (!plan.do_reduce && plan.do_bcast && is_root) {
-        // pure broadcast: the root publishes its tensor chunk by chunk
-        for (long long j0 = threadIdx.x; j0 < pc; j0 += (long long)kThreads * kUnroll) {
+        // pure broadcast: the root publishes its tensor chunk by chunk (in place there is nothing to copy)
+        for (long long j0 = threadIdx.x; j0 < pc && !plan.zero_copy; j0 += (long long)kThreads * kUnroll) {
           float f[kUnroll][kEpp];
 #pragma unroll
           for (int u = 0; u < kUnroll; ++u) {
@@ -185,7 +187,7 @@ __device__ __forceinline__ void tree_collective_body(const DevComm& c, const Tre
           wait_flag64(c, c.flag[role.parent] + ((role.flags & TR_PARENT_IS_ROOT) ? 1 : 2) * kMaxBlocks + lane, token);
         __syncthreads();
         const bool publish = role.flags & TR_PUBLISH;
-        const bool want = role.flags & TR_WANT_RESULT;
+        const bool want = (role.flags & TR_WANT_RESULT) && !(plan.zero_copy && publish);
         const char* src = c.data[role.parent];
         constexpr int UB = 8;
         for (long long j0 = threadIdx.x; j0 < pc; j0 += (long long)kThreads * UB) {

@@ -60,9 +60,11 @@ class Block(nn.Module):
         self.ln_2 = FusedLayerNorm(d, eps=cfg.layer_norm_epsilon)
         self.c_fc = FusedLinear(d, 4 * d)
         self.c_proj2 = FusedLinear(4 * d, d)
-        # experimental: c_fc + bias + GELU as ONE tcgen05 GEMM (ops/gemm.py); off unless asked for
-        # 1: forward fusion only (validated kernel); 2: also dGELU in the backward GEMM's epilogue (first run pending)
-        self.tc_mlp = int(os.environ.get("ADAPCC_TCGEN05_MLP", "0") or 0)
+        # the MLP's activation passes live in our tcgen05 GEMM's epilogues (ops/gemm.py, csrc/gemm_tcgen05_pp.cu):
+        # 2 (default): c_fc + bias + GELU forward AND dGELU + the c_fc bias gradient in the backward GEMM dY.W2 — no
+        #    stand-alone GELU / GELU-backward / column-sum kernel (measured -0.32 ms per GPT-2 step on B200);
+        # 1: forward fusion only; 0: cuBLAS + separate activation kernels
+        self.tc_mlp = int(os.environ.get("ADAPCC_TCGEN05_MLP", "2") or 0)
 
     def _mlp(self, h: torch.Tensor) -> torch.Tensor:
         if self.tc_mlp and h.is_cuda and h.dtype == torch.bfloat16 and torch.is_grad_enabled():

@@ -106,7 +106,10 @@ class FlatDataParallel:
         else:
             self.flat_param = torch.zeros(total, dtype=param_dtype, device=dev)
         self.zero_copy = False
-        if comm is not None and world_size > 1 and comm.heap_bytes >= total * esize + 4096:
+        # ADAPCC_FORCE_HEAP=1: gradients in the symmetric heap at world size 1 too (diagnostic: isolates the cost of
+        # producing gradients into peer-mapped / multicast-bound memory from the cost of the collectives themselves)
+        force_heap = os.environ.get("ADAPCC_FORCE_HEAP", "0") == "1"
+        if comm is not None and (world_size > 1 or force_heap) and comm.heap_bytes >= total * esize + 4096:
             self.flat_grad = comm.symm_empty(total, param_dtype)
             self.flat_grad.zero_()
             self.zero_copy = True

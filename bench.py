@@ -198,7 +198,7 @@ def main():
     if a.impl == "adapcc":
         AdapCC.init(args, local, rank, world)
         AdapCC.setup(ALLREDUCE)
-        comm = AdapCC.communicator.native if world > 1 else None
+        comm = AdapCC.communicator.native if (world > 1 or os.environ.get("ADAPCC_FORCE_HEAP") == "1") else None
     elif world > 1:
         def comm_fn(seg):                           # NCCL baseline on the same engine / buckets
             dist.all_reduce(seg, op=dist.ReduceOp.AVG)

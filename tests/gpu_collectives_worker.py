@@ -245,6 +245,23 @@ def main():
                   torch.float32, None, world * 2)
         dist.barrier()
         small.close()
+    # ---- strategy trees on heap tensors: reduced / broadcast in place (no staging pass) ---------------------------
+    comm.load_strategy("<trees>" + "".join(
+        "<root id='%d' ip='h'>%s</root>" % (o[0], "".join("<gpu id='%d' ip='h'>" % r for r in o[1:]) + "</gpu>" * (world - 1))
+        for o in (list(range(world)), list(reversed(range(world))))) + "</trees>")
+    for dtype in (torch.float32, torch.bfloat16):
+        for n, chunk in [(4096, 1024), ((1 << 20) + 8, 1 << 16)]:
+            seed += 1
+            comm.heap_reset()
+            t = comm.symm_empty(n, dtype)
+            t.copy_(gen(rank, n, dtype, seed).to(dev))
+            torch.cuda.synchronize()
+            dist.barrier()
+            comm.tree_collective(ALLREDUCE, t, op="sum", chunk_bytes=chunk)
+            comm.check()
+            check(f"tree in-place allreduce {dtype} n={n}", t, ref_reduce(world, n, dtype, seed, "sum", all_ranks), dtype,
+                  dtype if dtype != torch.float32 else None, world * 2)
+            dist.barrier()
     # ---- reduce-to-root and broadcast (direct) ---------------------------------------
     for root in sorted({0, world - 1}):
         for algo in algos:
@@ -514,6 +531,8 @@ def main():
             row["bf16wire_auto"] = timeit(lambda: comm.all_reduce(x, algo="auto", wire="bfloat16"), iters)
             if nbytes >= (1 << 16):
                 row["tree"] = timeit(lambda: comm.tree_collective(ALLREDUCE, x, chunk_bytes=4 << 20), iters)
+                if hz is not None:
+                    row["tree_zc"] = timeit(lambda: comm.tree_collective(ALLREDUCE, hz, chunk_bytes=4 << 20), iters)
             comm.check()
             results.append(row)
             if rank == 0:

@@ -114,3 +114,33 @@ def test_concurrent_ranks_always_agree_on_the_active_set():
         sizes.add(len(next(iter(sets))))
     assert min(sizes) < world                                    # lateness did produce relay steps
     assert len(c._steps) <= c.keep_steps + 1
+
+
+def test_dead_rank_is_not_waited_for_again():
+    """A rank that misses the heartbeat deadline once is declared dead: the survivors get status 0 with the survivor
+    list for that step, and every LATER step is decided among the survivors without running the fault timeout again."""
+    import threading
+    import time
+
+    from adapcc_b200.coord import Coordinator
+
+    c = Coordinator(world_size=3, relay_threshold=0.05, fault_tolerant_time=0.4)
+    out = {}
+
+    def survivor(rank, step):
+        out[(rank, step, "hook")] = c.hook(step, rank)
+        out[(rank, step, "ctl")] = c.controller(step, rank)
+
+    t0 = time.time()
+    ts = [threading.Thread(target=survivor, args=(r, 5)) for r in (0, 1)]       # rank 2 never reports
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert out[(0, 5, "ctl")][1] == 0 and sorted(out[(0, 5, "ctl")][0]) == [0, 1]
+    assert c.dead == {2} and time.time() - t0 >= 0.35
+    t1 = time.time()
+    ts = [threading.Thread(target=survivor, args=(r, 6)) for r in (0, 1)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert time.time() - t1 < 0.3, "the next step waited for the dead rank again"
+    assert out[(0, 6, "ctl")] == ([0, 1], 1) or sorted(out[(0, 6, "ctl")][0]) == [0, 1]
+    assert sorted(out[(1, 6, "hook")]) == [0, 1]
