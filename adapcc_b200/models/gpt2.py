@@ -201,7 +201,8 @@ class GPT2DoubleHeads(nn.Module):
         # batches score only the last candidate's reply, i.e. ~1/8 of the rows at the bench shape.
         self.lm_row_capacity = 0
         # residual adds fused into the following LayerNorm (fwd) / its input gradient (bwd)
-        self.fuse_add_ln = os.environ.get("ADAPCC_FUSE_ADD_LN", "0") == "1"
+        # (default on since the fused tcgen05 MLP: A/B in one gpurun call 8.53 vs 8.58-8.66 ms per step)
+        self.fuse_add_ln = os.environ.get("ADAPCC_FUSE_ADD_LN", "1") == "1"
         # wte[ids] + wpe[pos] + wte[token types] as one kernel, sort-free fp32-accumulating backward
         # (csrc/ops_embed.cu); the flat engine gives both tables a gradient sink (parallel/engine.py)
         self.fused_embed = os.environ.get("ADAPCC_FUSED_EMBED", "1") != "0"

@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--ref_precision", default="bf16", choices=["bf16", "tf32", "fp32"],
                     help="--impl reference only: bf16 autocast (default, the dtype of the comparison), or the script's "
                          "literal fp32 (optionally with TF32 matmuls)")
+    ap.add_argument("--relay_control", action="store_true",
+                    help="--engine ddp only: negotiate the active set with the coordinator every step (straggler / relay "
+                         "control, the reference's cuda_allreduce_hook behaviour); off by default in the bench")
     ap.add_argument("--allow_cpu", action="store_true", help="--impl reference only: gloo/CPU plumbing test")
     ap.add_argument("--no_nccl_arm", action="store_true",
                     help="skip the in-process NCCL arm (same engine, same buckets) that fills vs_baseline at N > 1")
@@ -190,7 +193,7 @@ def main():
     args = SimpleNamespace(port=5000, strategy_file=os.path.join(work, "strategy", f"bench_{world}.xml"),
                            logical_graph=os.path.join(work, "topology", f"logical_graph_{world}.xml"),
                            entry_point=a.entry_point, parallel_degree=min(4, world), profile_freq=500,
-                           work_dir=work, relay_control=False, algo=a.algo,
+                           work_dir=work, relay_control=bool(a.relay_control and a.engine == "ddp"), algo=a.algo,
                            heap_mb=((2 if a.zero1 else 1) * grad_bytes >> 20) + 64, staging_mb=64, backend="nccl")
     comm = None
     comm_fn = None
@@ -350,7 +353,9 @@ def main():
                        "seq_len": seq, "parallelism": f"dp{world}", "engine": a.engine, "algo": a.algo,
                        "optimizer": "adamw+clip1.0 (fused)", "grad_dtype": "bf16", "zero_copy_grads": zero_copy,
                        "buckets": n_buckets, "zero1": bool(engine is not None and getattr(engine, "zero1", False)),
-                       "lm_rows": a.lm_rows, "lm_chunk_rows": cfg.lm_chunk_rows,
+                       "lm_rows": a.lm_rows, "lm_chunk_rows": cfg.lm_chunk_rows, "relay_control": bool(a.relay_control and a.engine == "ddp"),
+                       "mlp": {0: "cublas + activation kernels", 1: "tcgen05 fused fwd", 2: "tcgen05 fused fwd+bwd"}.get(
+                           getattr(model.module.h[0] if hasattr(model, "module") else model.h[0], "tc_mlp", 0), "?"),
                        "fuse_add_ln": bool(getattr(model, "fuse_add_ln", False)),
                        "l2": "working set (params+grads+optimizer state ~2 GB/step) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": tokens_per_step / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e,
