@@ -14,6 +14,9 @@
 //   * four epilogue warps (one per scheduler) could not hide the TMEM-load / SFU / store latencies -> eight, and GELU
 //     costs one MUFU (tanh.approx) instead of two (ex2 + rcp).
 //
+// (The epilogue stages 32 columns at a time through ONE padded tile per warp, which leaves room for six 32 KB operand
+// stages: with four, the MMA issuer waited on `full[s]` half the time — ncu: tensor pipe 51 %, epilogue idle on acc_full.)
+//
 // Roles in each CTA of a pair (320 threads): warp 0 lane 0 = TMA producer (its 128 rows of A and of W per 64-wide
 // K slab, completion counted on the LEADER's `full` barrier); warp 1 = TMEM allocation and, in the leader, lane 0 = the
 // MMA issuer (4 x tcgen05.mma.cta_group::2 M256 x N256 x K16 per slab; tcgen05.commit multicast releases the slab in
@@ -33,14 +36,15 @@ namespace tc3 {
 
 constexpr int kBK = 64;            // K slab: 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kStages = 4;
+constexpr int kStages = 6;          // 6 x 32 KB per CTA: the refill round trip (MMA done -> commit -> producer wake -> TMA ->
+                                   // complete_tx -> issuer wake, ~3300 cycles measured) must fit in (stages - 1) x 512 MMA cycles
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kTileM = 256, kTileN = 256;       // per pair
 constexpr uint32_t kABytes = 128 * kBK * 2, kBBytes = 128 * kBK * 2, kStageBytes = kABytes + kBBytes;   // per CTA
-constexpr uint32_t kRowPitch = 144;             // staging row: 64 bf16 (128 B) + 16 B pad -> conflict-free both ways
-constexpr uint32_t kStageTile = 32 * kRowPitch; // one warp's 32 x 64 chunk
-constexpr uint32_t kEpiBytes = kEpiWarps * 2 * kStageTile;
+constexpr uint32_t kRowPitch = 80;              // staging row: 32 bf16 (64 B) + 16 B pad: row writes conflict-free
+constexpr uint32_t kStageTile = 32 * kRowPitch; // one warp's 32 x 32 chunk; ONE tile per warp, reused for out / pre / aux
+constexpr uint32_t kEpiBytes = kEpiWarps * kStageTile;
 constexpr uint32_t kBiasBytes = kEpiWarps * 128 * 4;            // each epilogue warp's 128 bias values of the tile, as fp32
 constexpr uint32_t kBarOffset = kStages * kStageBytes + kEpiBytes + kBiasBytes;
 // full[S] empty[S] acc_full[2] acc_empty[2] + tmem slot
@@ -179,12 +183,12 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) {
   return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
 }
 
-// One warp moves its staged 32 x 64 bf16 chunk to / from global memory, 4 rows (4 x 128 B) per instruction.
+// One warp moves its staged 32 x 32 bf16 chunk to / from global memory, 8 rows (8 x 64 B) per instruction.
 __device__ __forceinline__ void chunk_to_global(uint32_t stage, __nv_bfloat16* __restrict__ g, size_t ld, int row0,
                                                 int rows_valid, int lane) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + (lane >> 3), ch = lane & 7;
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2), ch = lane & 3;
     const uint4 v = ld_shared_v4(stage + (uint32_t)r * kRowPitch + (uint32_t)ch * 16);
     if (r < rows_valid) *reinterpret_cast<uint4*>(g + (size_t)(row0 + r) * ld + ch * 8) = v;
   }
@@ -192,8 +196,8 @@ __device__ __forceinline__ void chunk_to_global(uint32_t stage, __nv_bfloat16* _
 __device__ __forceinline__ void chunk_from_global(uint32_t stage, const __nv_bfloat16* __restrict__ g, size_t ld,
                                                   int row0, int rows_valid, int lane) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + (lane >> 3), ch = lane & 7;
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2), ch = lane & 3;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (r < rows_valid) v = __ldg(reinterpret_cast<const uint4*>(g + (size_t)(row0 + r) * ld + ch * 8));
     st_shared_v4(stage + (uint32_t)r * kRowPitch + (uint32_t)ch * 16, v);
@@ -291,8 +295,8 @@ gemm_pair_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
   } else {
     // ===== epilogue: 8 warps, TMEM lane quarter q, column half h =====
     const int e = warp - 2, q = warp & 3, half = e >> 2;
-    const uint32_t st_out = base + kStages * kStageBytes + (uint32_t)e * 2 * kStageTile, st_aux = st_out + kStageTile;
-    const uint32_t my_row = st_out + (uint32_t)lane * kRowPitch, my_row_aux = st_aux + (uint32_t)lane * kRowPitch;
+    const uint32_t st = base + kStages * kStageBytes + (uint32_t)e * kStageTile;     // this warp's 32 x 32 staging tile
+    const uint32_t my_row = st + (uint32_t)lane * kRowPitch;
     const uint32_t st_bias = base + kStages * kStageBytes + kEpiBytes + (uint32_t)e * 512;
     uint32_t local = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
@@ -316,73 +320,74 @@ gemm_pair_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
       mbar_wait(acc_full(as), use & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int col0 = n_blk * kTileN + half * 128 + cc * 64;
-        if (ACT == 2) {                                             // aux (saved pre-activation) chunk, coalesced
-          chunk_from_global(st_aux, pre + col0, (size_t)N, row0, rows_valid, lane);
+      for (int cc = 0; cc < 4; ++cc) {                              // 32-column groups of this warp's 128-column half
+        const int col0 = n_blk * kTileN + half * 128 + cc * 32;
+        uint32_t ax[16];
+        if (ACT == 2) {
+          // aux (saved pre-activation): coalesced global -> staging, then every lane takes its own row
+          chunk_from_global(st, pre + col0, (size_t)N, row0, rows_valid, lane);
           __syncwarp();
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t acc[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)kTileN + (uint32_t)(half * 128 + cc * 64 + h * 32), acc);
-          uint32_t po[16], pp[16];
-          if (ACT == 2) {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const uint4 ax = ld_shared_v4(my_row_aux + (uint32_t)h * 64 + (uint32_t)v * 16);
-              const uint32_t aw[4] = {ax.x, ax.y, ax.z, ax.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 a2 = unpack_bf16x2(aw[j]);
-                const int i = v * 4 + j;
-                po[i] = pack_bf16x2(__uint_as_float(acc[2 * i]) * gelu_tanh_grad(a2.x),
-                                    __uint_as_float(acc[2 * i + 1]) * gelu_tanh_grad(a2.y));
-              }
-            }
-          } else {
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              float4 b4;
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
-                           : "r"(st_bias + (uint32_t)(cc * 64 + h * 32 + v * 4) * 4) : "memory");
-              const float r0 = __uint_as_float(acc[4 * v]) + b4.x, r1 = __uint_as_float(acc[4 * v + 1]) + b4.y;
-              const float r2 = __uint_as_float(acc[4 * v + 2]) + b4.z, r3 = __uint_as_float(acc[4 * v + 3]) + b4.w;
-              pp[2 * v] = pack_bf16x2(r0, r1);
-              pp[2 * v + 1] = pack_bf16x2(r2, r3);
-              if (ACT == 1) {       // GELU on the fp32 pre-activation (torch applies it to the bf16-rounded one: the two
-                                    // differ by less than the output's own bf16 rounding)
-                po[2 * v] = pack_bf16x2(gelu_tanh(r0), gelu_tanh(r1));
-                po[2 * v + 1] = pack_bf16x2(gelu_tanh(r2), gelu_tanh(r3));
-              } else {
-                po[2 * v] = pp[2 * v];
-                po[2 * v + 1] = pp[2 * v + 1];
-              }
-            }
-          }
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
-            st_shared_v4(my_row + (uint32_t)h * 64 + (uint32_t)v * 16, make_uint4(po[4 * v], po[4 * v + 1], po[4 * v + 2], po[4 * v + 3]));
-            if (ACT <= 1 && pre != nullptr)
-              st_shared_v4(my_row_aux + (uint32_t)h * 64 + (uint32_t)v * 16, make_uint4(pp[4 * v], pp[4 * v + 1], pp[4 * v + 2], pp[4 * v + 3]));
+            const uint4 t = ld_shared_v4(my_row + (uint32_t)v * 16);
+            ax[4 * v] = t.x; ax[4 * v + 1] = t.y; ax[4 * v + 2] = t.z; ax[4 * v + 3] = t.w;
+          }
+          __syncwarp();                                             // the staging tile is about to hold `out`
+        }
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)kTileN + (uint32_t)(half * 128 + cc * 32), acc);
+        uint32_t po[16], pp[16];
+        if (ACT == 2) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 a2 = unpack_bf16x2(ax[i]);
+            po[i] = pack_bf16x2(__uint_as_float(acc[2 * i]) * gelu_tanh_grad(a2.x),
+                                __uint_as_float(acc[2 * i + 1]) * gelu_tanh_grad(a2.y));
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            float4 b4;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
+                         : "r"(st_bias + (uint32_t)(cc * 32 + v * 4) * 4) : "memory");
+            const float r0 = __uint_as_float(acc[4 * v]) + b4.x, r1 = __uint_as_float(acc[4 * v + 1]) + b4.y;
+            const float r2 = __uint_as_float(acc[4 * v + 2]) + b4.z, r3 = __uint_as_float(acc[4 * v + 3]) + b4.w;
+            pp[2 * v] = pack_bf16x2(r0, r1);
+            pp[2 * v + 1] = pack_bf16x2(r2, r3);
+            if (ACT == 1) {         // GELU on the fp32 pre-activation (torch applies it to the bf16-rounded one: the two
+                                    // differ by less than the output's own bf16 rounding)
+              po[2 * v] = pack_bf16x2(gelu_tanh(r0), gelu_tanh(r1));
+              po[2 * v + 1] = pack_bf16x2(gelu_tanh(r2), gelu_tanh(r3));
+            } else {
+              po[2 * v] = pp[2 * v];
+              po[2 * v + 1] = pp[2 * v + 1];
+            }
           }
         }
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          st_shared_v4(my_row + (uint32_t)v * 16, make_uint4(po[4 * v], po[4 * v + 1], po[4 * v + 2], po[4 * v + 3]));
         __syncwarp();
-        chunk_to_global(st_out, out + col0, (size_t)N, row0, rows_valid, lane);
-        if (ACT <= 1 && pre != nullptr) chunk_to_global(st_aux, pre + col0, (size_t)N, row0, rows_valid, lane);
+        chunk_to_global(st, out + col0, (size_t)N, row0, rows_valid, lane);
         if (ACT == 2 && colsum != nullptr) {
-          // bias gradient: lane l sums columns 2l, 2l+1 of the staged bf16 chunk over the valid rows
-          float s0 = 0.f, s1 = 0.f;
+          // bias gradient: lane l sums column l of the staged bf16 chunk over the valid rows
+          float s0 = 0.f;
           for (int r = 0; r < rows_valid; ++r) {
-            uint32_t w;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(st_out + (uint32_t)r * kRowPitch + (uint32_t)lane * 4));
-            const float2 f = unpack_bf16x2(w);
-            s0 += f.x; s1 += f.y;
+            unsigned short w;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w) : "r"(st + (uint32_t)r * kRowPitch + (uint32_t)lane * 2));
+            s0 += __uint_as_float((uint32_t)w << 16);
           }
-          atomicAdd(colsum + col0 + 2 * lane, s0);
-          atomicAdd(colsum + col0 + 2 * lane + 1, s1);
+          atomicAdd(colsum + col0 + lane, s0);
         }
-        __syncwarp();                                               // staging is reused by the next chunk
+        __syncwarp();                                               // everybody has read the tile: reuse it
+        if (ACT <= 1 && pre != nullptr) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            st_shared_v4(my_row + (uint32_t)v * 16, make_uint4(pp[4 * v], pp[4 * v + 1], pp[4 * v + 2], pp[4 * v + 3]));
+          __syncwarp();
+          chunk_to_global(st, pre + col0, (size_t)N, row0, rows_valid, lane);
+          __syncwarp();
+        }
       }
       tc_fence_before();
       __syncwarp();

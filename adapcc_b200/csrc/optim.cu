@@ -20,6 +20,14 @@ template <> __device__ __forceinline__ float ldf<float>(const float* p, long lon
 template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
 
 // ---- sum of squares ---------------------------------------------------------------------------
+// DETERMINISTIC: every block writes its partial sum to a slot, the last block to finish adds the slots in index order
+// and does ONE read-modify-write of `out`. (A float atomicAdd per block made the grad norm — and through the clip
+// coefficient every parameter — depend on block scheduling: data-parallel replicas drifted apart by one bf16 ulp on
+// ~1e-6 of the elements per step although their gradients were bit-identical; found with tools/replica_debug_worker.py.)
+constexpr int kSumsqMaxBlocks = 592;
+__device__ float g_sumsq_partials[kSumsqMaxBlocks];
+__device__ unsigned int g_sumsq_ticket = 0;
+
 template <typename T>
 __global__ void __launch_bounds__(512) sumsq_kernel(const T* __restrict__ g, long long n, float* __restrict__ out) {
   constexpr int kVec = 16 / sizeof(T);
@@ -44,7 +52,18 @@ __global__ void __launch_bounds__(512) sumsq_kernel(const T* __restrict__ g, lon
     float v = threadIdx.x < (blockDim.x >> 5) ? warp_sum[threadIdx.x] : 0.f;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) atomicAdd(out, v);
+    if (threadIdx.x == 0) {
+      g_sumsq_partials[blockIdx.x] = v;
+      __threadfence();
+      const unsigned int t = atomicAdd(&g_sumsq_ticket, 1u);
+      if (t == gridDim.x - 1) {                       // last block: fixed-order total
+        __threadfence();
+        float total = 0.f;
+        for (unsigned int b = 0; b < gridDim.x; ++b) total += *((volatile float*)&g_sumsq_partials[b]);
+        *out += total;                                // launches of one stream are serialised: a plain RMW is enough
+        g_sumsq_ticket = 0;
+      }
+    }
   }
 }
 
@@ -147,7 +166,7 @@ int adapcc_sumsq(const void* g, long long n, int dtype, float* out, void* stream
   cudaStream_t s = (cudaStream_t)stream;
   if (n <= 0) return 0;
   if (reinterpret_cast<uintptr_t>(g) & 15) { set_error("sumsq: pointer must be 16-byte aligned"); return -1; }
-  int blocks = (int)std::min<long long>(592, (n / 8 + 511) / 512);
+  int blocks = (int)std::min<long long>(kSumsqMaxBlocks, (n / 8 + 511) / 512);
   if (blocks < 1) blocks = 1;
   if (dtype == F32) sumsq_kernel<float><<<blocks, 512, 0, s>>>((const float*)g, n, out);
   else if (dtype == BF16) sumsq_kernel<__nv_bfloat16><<<blocks, 512, 0, s>>>((const __nv_bfloat16*)g, n, out);

@@ -138,14 +138,26 @@ class FlatDataParallel:
         cap = max(1, int(bucket_mb * (1 << 20) / esize))
         self.buckets: List[_Bucket] = []
         self._bucket_of: Dict[int, int] = {}
+        # Embedding tables (marked by the model) get a bucket of their own: their gradient is final only after the very
+        # last op of the backward pass, so everything that shares their bucket would be reduced in the exposed tail too.
+        def is_tail(j: int) -> bool:
+            return bool(getattr(params[j], "_adapcc_embed_table", False))
+
         end, members = total, []
         for i in range(len(params) - 1, -1, -1):
             members.append(i)
             start = self._offsets[i]
-            if end - start >= cap or i == 0:
-                for j in members:
-                    self._bucket_of[j] = len(self.buckets)
-                self.buckets.append(_Bucket(start, end, len(members)))
+            boundary = i > 0 and is_tail(i - 1) != is_tail(i)
+            if end - start >= cap or i == 0 or boundary:
+                if boundary and end - start < cap // 4 and self.buckets and not is_tail(i):
+                    last = self.buckets[-1]                 # a small remainder in front of the tail: no bucket of its own
+                    last.start, last.n_params = start, last.n_params + len(members)
+                    for j in members:
+                        self._bucket_of[j] = len(self.buckets) - 1
+                else:
+                    for j in members:
+                        self._bucket_of[j] = len(self.buckets)
+                    self.buckets.append(_Bucket(start, end, len(members)))
                 end, members = start, []
         # ZeRO-1 slices: the direct kernels cut a message into world slices of ceil(packs / world) 16-byte
         # packs (csrc/kernels_direct.cuh::Partition); rank r owns slice r of every bucket
@@ -181,6 +193,8 @@ class FlatDataParallel:
                     p._adapcc_grad_sink = sink
                     self._sinks.append(sink)
         self.direct_grads = bool(self._sinks)
+        self._debug = os.environ.get("ADAPCC_ENGINE_DEBUG", "0") == "1"
+        self._ready: List[bool] = [False] * len(params)
         self.comm_stream = torch.cuda.Stream(device=dev, priority=-1) if dev.type == "cuda" else None
         self._graph = None
         self._static: Dict[str, torch.Tensor] = {}
@@ -190,8 +204,21 @@ class FlatDataParallel:
 
     # -- gradient hooks ---------------------------------------------------------------------------
     def _grad_ready(self, i: int) -> None:
+        """Parameter ``i``'s gradient is final in the flat buffer. Reported by the autograd post-accumulate hook or,
+        for parameters whose fused op writes the gradient itself, by the op's sink. BOTH can fire for one parameter: the
+        op returns ``None`` for it, and this torch still runs the parameter's AccumulateGrad node (and its hooks) with
+        the undefined gradient right after the op's backward. Only the first report of a step counts — counting both
+        launched every bucket after HALF of its gradients (found in round 2 with tools/engine_debug_worker.py: gradients
+        produced after the early launch were never averaged)."""
+        if self._ready[i]:
+            return
+        self._ready[i] = True
         b = self.buckets[self._bucket_of[i]]
         b.pending -= 1
+        if self._debug and b.pending == 0:
+            names = {id(p): n for n, p in self.model.named_parameters()}
+            print(f"[engine] bucket {self._bucket_of[i]} ({b.n_params} params) launched by "
+                  f"{names.get(id(self.params[i]), i)} after {sum(self._ready)} ready reports", flush=True)
         if b.pending == 0:
             self._launch_bucket(b)
 
@@ -223,6 +250,7 @@ class FlatDataParallel:
 
         self.flat_grad.zero_()
         self._forked = False
+        self._ready = [False] * len(self.params)
         for b in self.buckets:
             b.pending = b.n_params
         for sink in self._sinks:

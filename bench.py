@@ -325,6 +325,15 @@ def main():
 
     if comm is not None:
         AdapCC.communicator.synchronize()
+    replicas_identical = None
+    if world > 1 and engine is not None:
+        # data-parallel invariant after K + warm-up steps: every rank holds bit-identical parameters (a gradient that
+        # missed its bucket's all-reduce would break it)
+        hi, lo = engine.flat_param.float(), engine.flat_param.float()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        replicas_identical = bool(torch.equal(hi, lo))
+        del hi, lo
     # ---- (3) in-process baseline arm: the SAME engine, buckets and graph over NCCL's all-reduce ----------
     ms_nccl = None
     if a.impl == "adapcc" and world > 1 and engine is not None and use_graph and not a.no_nccl_arm and not engine.zero1:
@@ -364,6 +373,8 @@ def main():
         }
         if allreduce_check is not None:
             out["allreduce_check"] = allreduce_check
+        if replicas_identical is not None:
+            out["replicas_identical"] = replicas_identical
         if ms_nccl:
             # BASELINE.md publishes no tokens/s; the practical baseline it names is "the reference-side NCCL on the
             # same box": the same engine/buckets/graph with torch.distributed's NCCL all-reduce, timed in this process

@@ -48,6 +48,9 @@ def main():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--out", default="")
+    ap.add_argument("--sweep_max_log2", type=int, default=0, help="largest sweep message (log2 bytes); 0: 26 quick / 28 full")
+    ap.add_argument("--sweep_step", type=int, default=0, help="log2 step between sweep sizes; 0: 2 quick / 1 full")
+    ap.add_argument("--no_blocks_sweep", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -475,7 +478,8 @@ def main():
     results = []
     if args.sweep:
         comm.load_strategy(strategies["binary"])
-        sweep_sizes = [1 << p for p in range(10, 29 if not args.quick else 27, 2 if args.quick else 1)]  # bytes
+        top = args.sweep_max_log2 or (26 if args.quick else 28)
+        sweep_sizes = [1 << p for p in range(10, top + 1, args.sweep_step or (2 if args.quick else 1))]  # bytes
         side = torch.cuda.Stream()
 
         def timeit(fn, iters, graph=True):
@@ -542,7 +546,7 @@ def main():
                     flush=True)
         # reduce / broadcast / all-to-all next to NCCL (nccl-tests' reduce, broadcast and alltoall,
         # /root/reference/nccl-perf/benchmark/src/{reduce,broadcast,alltoall}.cu; busbw factor 1, resp. (n-1)/n)
-        for nbytes in [1 << p for p in range(10, 29, 3 if args.quick else 2)]:
+        for nbytes in [1 << p for p in range(10, min(top, 28) + 1, 3 if args.quick else 2)]:
             n = nbytes // 4
             x = torch.randn(n, device=dev)
             iters = 40 if nbytes <= (1 << 22) else (10 if nbytes <= (1 << 26) else 4)
@@ -568,7 +572,7 @@ def main():
                     f"{k}={v * 1e6:7.1f}us({nbytes * (fa if k.startswith('a2a') else 1.0) / v / 1e9:6.1f})"
                     for k, v in row.items() if k not in ("bytes", "prims")), flush=True)
         # CTA-count sensitivity at large sizes (zero-copy paths)
-        for nbytes in [1 << 24, 1 << 26]:
+        for nbytes in ([] if args.no_blocks_sweep else [1 << 24, 1 << 26]):
             n = nbytes // 4
             comm.heap_reset()
             hz = comm.symm_empty(n, torch.float32)

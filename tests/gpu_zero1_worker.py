@@ -17,13 +17,16 @@ from adapcc_b200.runtime.native import NativeComm  # noqa: E402
 from adapcc_b200.runtime.rendezvous import unique_name  # noqa: E402
 
 
-def run(comm, rank, world, dev, zero1, graph, steps=8, lr=2e-3):
+def run(comm, rank, world, dev, zero1, graph, steps=8, lr=2e-3, nccl=False, info=None):
     cfg = GPT2Config(vocab_size=1000, n_positions=64, n_embd=256, n_layer=2, n_head=4, lm_chunk_rows=128)
     torch.manual_seed(7)
     model = GPT2DoubleHeads(cfg).to(dev)
     comm.heap_reset()
-    eng = FlatDataParallel(model, comm, world_size=world, rank=rank, lr=lr, max_norm=1.0, bucket_mb=0.5,
-                           zero1=zero1)
+    comm_fn = (lambda seg: dist.all_reduce(seg, op=dist.ReduceOp.AVG)) if nccl else None
+    eng = FlatDataParallel(model, None if nccl else comm, world_size=world, rank=rank, lr=lr, max_norm=1.0, bucket_mb=0.5,
+                           zero1=zero1, comm_fn=comm_fn)
+    if info is not None:
+        info["buckets"] = [(b.start, b.end) for b in eng.buckets]
     assert eng.zero1 == zero1
     batches = [synthetic_batch(2, 2, 64, cfg.vocab_size, device=dev, seed=100 * rank + i) for i in range(3)]
     losses = []
@@ -51,8 +54,21 @@ def main():
         # (1) ONE step from identical weights: the two modes compute the same update (same averaged gradients, same
         # clip coefficient, same AdamW) on different ranks -> parameters agree except where a rounding-level gradient
         # difference (fp32 atomics order in the embedding backward) flips Adam's first-step sign on a near-zero element
-        _, base_p = run(comm, rank, world, dev, zero1=False, graph=graph, steps=1)
+        info = {}
+        _, base_p = run(comm, rank, world, dev, zero1=False, graph=graph, steps=1, info=info)
         _, z_p = run(comm, rank, world, dev, zero1=True, graph=graph, steps=1)
+        _, n_p = run(comm, rank, world, dev, zero1=False, graph=graph, steps=1, nccl=True)
+        if rank == 0:
+            from adapcc_b200.parallel.engine import shard_of
+            print(f"[zero1] graph={graph} vs NCCL reference: plain-DP params off (>2e-4) "
+                  f"{float(((base_p - n_p).abs() > 2e-4).float().mean()):.2e}, zero1 off "
+                  f"{float(((z_p - n_p).abs() > 2e-4).float().mean()):.2e}", flush=True)
+            for bi, (lo, hi) in enumerate(info["buckets"]):
+                row = []
+                for r in range(world):
+                    a, b = shard_of(lo, hi, r, world, 8)
+                    row.append("%.2f" % float(((z_p[a:b] - n_p[a:b]).abs() > 2e-4).float().mean()) if b > a else "-")
+                print(f"[zero1]   bucket {bi} [{lo},{hi}) zero1-vs-NCCL off fraction per owner slice: {row}", flush=True)
         diff = (z_p - base_p).abs()
         frac_off = float((diff > 2e-4).float().mean())
         ref = z_p.clone()

@@ -30,8 +30,32 @@ def test_collectives_multi_gpu():
     assert "failures: 0" in r.stdout, tail
 
 
-@pytest.mark.skipif(os.environ.get("ADAPCC_EXPERIMENTAL", "0") != "1",
-                    reason="sharded-optimizer mode has not had its first GPU run: set ADAPCC_EXPERIMENTAL=1")
+def _torchrun(worker, world, timeout=600, *args):
+    env = dict(os.environ, ADAPCC_TIMEOUT_MS="15000")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "tests", worker), *args]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    return r, (r.stdout + r.stderr)[-4000:]
+
+
+def test_engine_gradients_are_the_average_of_the_local_gradients():
+    """The flat engine's bucketed all-reduce (sinks + hooks + side stream, eager and graph) against NCCL."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r, tail = _torchrun("gpu_engine_parity_worker.py", 4 if n >= 4 else 2)
+    assert r.returncode == 0, tail
+    assert "wrong averaged gradients: 0 of" in r.stdout, tail
+
+
+def test_flag_protocol_soak():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r, tail = _torchrun("gpu_soak_worker.py", 4 if n >= 4 else 2, 600, "--ops", "3000")
+    assert r.returncode == 0 and "failures: 0" in r.stdout, tail
+
+
 def test_zero1_engine_matches_data_parallel():
     n = torch.cuda.device_count()
     if n < 2:

@@ -1,0 +1,15 @@
+#!/bin/bash
+# round 2, call 10 (2 GPUs): after the bucket-launch fix — gradient parity (engine vs NCCL average), ZeRO-1 parity,
+# honest N=1 / N=2 bench numbers (default, zero1, fewer comm CTAs), timelines.
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+timeout 200 $TR --master-port 29621 tests/gpu_engine_parity_worker.py > gpurun_out/c10_parity.log 2>&1; grep -E "parity|Error|Traceback" gpurun_out/c10_parity.log | head -12
+ADAPCC_TIMEOUT_MS=15000 timeout 400 $TR --master-port 29602 tests/gpu_zero1_worker.py > gpurun_out/c10_zero1.log 2>&1; grep -E "zero1" gpurun_out/c10_zero1.log | cut -c1-300 | head -24
+timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/c10_bench1.json 2> gpurun_out/c10_bench1.err; tail -1 gpurun_out/c10_bench1.json | cut -c1-230
+b() { n=$1; shift; env "$@" timeout 300 $TR --master-port 29603 bench.py --gpus 2 --steps 20 --warmup 5 $EXTRA > gpurun_out/c10_bench2_$n.json 2> gpurun_out/c10_bench2_$n.err; echo "$n: $(tail -1 gpurun_out/c10_bench2_$n.json | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print(round(d["ms_per_step"],3), round(d["e2e"]["ms_per_step"],3), d.get("vs_baseline"), d.get("allreduce_check"), d.get("replicas_identical"), d.get("baseline_arm",{}).get("ms_per_step"))' 2>&1 | tail -1)"; tail -1 gpurun_out/c10_bench2_$n.err | cut -c1-200; }
+EXTRA="" b default X=1
+EXTRA="--zero1 --no_nccl_arm" b zero1 X=1
+EXTRA="--no_nccl_arm" b blocks16 ADAPCC_MAX_BLOCKS=16
+EXTRA="--no_nccl_arm --bucket_mb 16" b bucket16 X=1
+timeout 200 $TR --master-port 29605 tools/torch_profile_ddp.py --out gpurun_out/c10_timeline_2.md > gpurun_out/c10_timeline2.log 2>&1; head -12 gpurun_out/c10_timeline_2.md | cut -c1-300
+timeout 200 $TR --master-port 29606 tools/torch_profile_ddp.py --zero1 --out gpurun_out/c10_timeline_2_zero1.md > gpurun_out/c10_timeline_z.log 2>&1; head -12 gpurun_out/c10_timeline_2_zero1.md | cut -c1-300
