@@ -46,9 +46,11 @@ def parse():
     ap.add_argument("--lm_rows", default="all", choices=["all", "scored"],
                     help="all: LM head on every position (reference behaviour, the default and the judged "
                          "number); scored: only rows whose label is not -100 (same loss and gradients)")
-    ap.add_argument("--zero1", action="store_true",
-                    help="opt-in sharded optimizer: reduce-scatter + AdamW with the parameter broadcast fused "
-                         "(multimem.st); N > 1 only; not the judged default")
+    ap.add_argument("--zero1", action="store_true", help="(default at N > 1; kept for old command lines)")
+    ap.add_argument("--no_zero1", action="store_true",
+                    help="replicated optimizer (all-reduce + full AdamW on every rank) instead of the default ZeRO-1 "
+                         "sharded optimizer (reduce-scatter + AdamW on 1/N slices with the parameter broadcast fused, "
+                         "multimem.st) at N > 1")
     ap.add_argument("--lm_chunk", type=int, default=0, help="rows per fused LM-head/CE chunk (0 = model default)")
     ap.add_argument("--tiny", action="store_true", help="tiny model (smoke tests only; never a bench value)")
     ap.add_argument("--ref_precision", default="bf16", choices=["bf16", "tf32", "fp32"],
@@ -194,7 +196,7 @@ def main():
                            logical_graph=os.path.join(work, "topology", f"logical_graph_{world}.xml"),
                            entry_point=a.entry_point, parallel_degree=min(4, world), profile_freq=500,
                            work_dir=work, relay_control=bool(a.relay_control and a.engine == "ddp"), algo=a.algo,
-                           heap_mb=((2 if a.zero1 else 1) * grad_bytes >> 20) + 64, staging_mb=64, backend="nccl")
+                           heap_mb=((1 if a.no_zero1 else 2) * grad_bytes >> 20) + 64, staging_mb=64, backend="nccl")
     comm = None
     comm_fn = None
     allreduce_check = None
@@ -251,7 +253,7 @@ def main():
     else:
         engine = FlatDataParallel(model, comm, world_size=world, rank=rank, bucket_mb=a.bucket_mb, lr=6.25e-5,
                                   max_norm=1.0, algo=a.algo, comm_fn=comm_fn,
-                                  zero1=(a.zero1 and world > 1 and comm is not None) or None)
+                                  zero1=False if a.no_zero1 else None)
         n_buckets, zero_copy = len(engine.buckets), engine.zero_copy
         if comm is not None and world > 1:
             # multi-GPU numerics of the kernel that is on the hot path, on the real bucket, against NCCL
@@ -323,6 +325,7 @@ def main():
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3) / a.steps)
     clocks = sampler.stop() if rank == 0 else {}
 
+    zero1_flag = bool(engine is not None and getattr(engine, "zero1", False))
     if comm is not None:
         AdapCC.communicator.synchronize()
     replicas_identical = None
@@ -336,9 +339,11 @@ def main():
         del hi, lo
     # ---- (3) in-process baseline arm: the SAME engine, buckets and graph over NCCL's all-reduce ----------
     ms_nccl = None
-    if a.impl == "adapcc" and world > 1 and engine is not None and use_graph and not a.no_nccl_arm and not engine.zero1:
+    if a.impl == "adapcc" and world > 1 and engine is not None and use_graph and not a.no_nccl_arm:
         def nccl_fn(seg):
             dist.all_reduce(seg, op=dist.ReduceOp.AVG)
+        zero1_used = bool(engine.zero1)
+        engine.zero1 = False                        # what stock data parallelism does: all-reduce + replicated AdamW
         engine.comm_fn = nccl_fn
         engine.capture(dev_batch, warmup=2)
         for _ in range(max(3, a.warmup)):
@@ -361,7 +366,7 @@ def main():
                        "global_batch": a.batch * world, "per_gpu_batch": a.batch, "candidates": a.candidates,
                        "seq_len": seq, "parallelism": f"dp{world}", "engine": a.engine, "algo": a.algo,
                        "optimizer": "adamw+clip1.0 (fused)", "grad_dtype": "bf16", "zero_copy_grads": zero_copy,
-                       "buckets": n_buckets, "zero1": bool(engine is not None and getattr(engine, "zero1", False)),
+                       "buckets": n_buckets, "zero1": zero1_flag,
                        "lm_rows": a.lm_rows, "lm_chunk_rows": cfg.lm_chunk_rows, "relay_control": bool(a.relay_control and a.engine == "ddp"),
                        "mlp": {0: "cublas + activation kernels", 1: "tcgen05 fused fwd", 2: "tcgen05 fused fwd+bwd"}.get(
                            getattr(model.module.h[0] if hasattr(model, "module") else model.h[0], "tc_mlp", 0), "?"),

@@ -9,12 +9,26 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_reference_arm_reports_unavailable():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1",
-                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 0, r.stderr
+def test_reference_arm_contract_on_cpu():
+    """Without a GPU the reference arm says so (one JSON line, exit 0); with ``--allow_cpu --tiny`` the same code path —
+    HuggingFace GPT2DoubleHeadsModel + torch DDP + AdamW + clip, the reference's step body — runs over gloo and prints
+    the full bench line without importing anything of this repository."""
+    import torch
+
+    base = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1"]
+    if not torch.cuda.is_available():
+        r = subprocess.run(base, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        rec = json.loads(r.stdout.strip().splitlines()[-1])
+        assert rec["impl"] == "reference" and "unavailable" in rec and len(rec["unavailable"]) > 20
+    r = subprocess.run(base + ["--tiny", "--allow_cpu", "--seq", "32"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES="", MASTER_PORT="29577"))
+    assert r.returncode == 0, r.stderr[-2000:]
     rec = json.loads(r.stdout.strip().splitlines()[-1])
-    assert rec["impl"] == "reference" and "unavailable" in rec and len(rec["unavailable"]) > 20
+    assert rec["impl"] == "reference" and rec["metric"] == "gpt2_small_ddp_train_tokens_per_sec" and rec["value"] > 0
+    assert rec["repo_code_on_path"] is False and "GPT2DoubleHeadsModel" in rec["reference_class"]
+    assert rec["e2e"]["h2d_bytes_per_step"] > 0 and rec["e2e"]["d2h_bytes_per_step"] == 4
+    assert rec["hyperparameters_from"]
 
 
 def test_graft_entry_build_and_exports():

@@ -30,7 +30,7 @@ def grads(mode):
     if mode == "local":          # no communication at all: the local gradients
         eng = FlatDataParallel(model, None, world_size=1, rank=0, lr=0.0, max_norm=0.0, bucket_mb=0.5)
     else:
-        eng = FlatDataParallel(model, comm, world_size=world, rank=rank, lr=0.0, max_norm=0.0, bucket_mb=0.5)
+        eng = FlatDataParallel(model, comm, world_size=world, rank=rank, lr=0.0, max_norm=0.0, bucket_mb=0.5, zero1=False)
     if rank != 0:
         eng._debug = False
     eng.step(batch)

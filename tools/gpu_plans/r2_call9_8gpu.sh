@@ -14,10 +14,10 @@ timeout 150 $TR --master-port 29721 tests/gpu_engine_parity_worker.py > gpurun_o
 ADAPCC_TIMEOUT_MS=15000 timeout 240 $TR --master-port 29722 tests/gpu_zero1_worker.py > gpurun_out/c9_zero1_$N.log 2>&1; grep -E "zero1\] (rank 0|failures)" gpurun_out/c9_zero1_$N.log | cut -c1-260 | head -6; lap parity
 b() { n=$1; shift; env "$@" timeout 240 $TR --master-port 29703 bench.py --gpus $N --steps 20 --warmup 5 $EXTRA > gpurun_out/c9_bench${N}_$n.json 2> gpurun_out/c9_bench${N}_$n.err; echo "$n: $(tail -1 gpurun_out/c9_bench${N}_$n.json | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print(round(d["ms_per_step"],3), round(d["e2e"]["ms_per_step"],3), d.get("vs_baseline"), d.get("allreduce_check"), d.get("replicas_identical"), d.get("baseline_arm",{}).get("ms_per_step"))' 2>&1 | tail -1)"; tail -1 gpurun_out/c9_bench${N}_$n.err | cut -c1-200; }
 EXTRA="" b default X=1
-EXTRA="--zero1 --no_nccl_arm" b zero1 X=1
+EXTRA="--no_zero1 --no_nccl_arm" b replicated X=1
 EXTRA="--impl reference" b reference X=1; lap bench
 timeout 150 $TR --master-port 29705 tools/torch_profile_ddp.py --out gpurun_out/c9_timeline_$N.md > gpurun_out/c9_timeline_$N.log 2>&1; head -3 gpurun_out/c9_timeline_$N.md | cut -c1-300
-timeout 150 $TR --master-port 29706 tools/torch_profile_ddp.py --zero1 --out gpurun_out/c9_timeline_${N}_zero1.md > gpurun_out/c9_timeline_${N}z.log 2>&1; head -3 gpurun_out/c9_timeline_${N}_zero1.md | cut -c1-300; lap timeline
+timeout 150 $TR --master-port 29706 tools/torch_profile_ddp.py --no_zero1 --out gpurun_out/c9_timeline_${N}_replicated.md > gpurun_out/c9_timeline_${N}z.log 2>&1; head -3 gpurun_out/c9_timeline_${N}_replicated.md | cut -c1-300; lap timeline
 ADAPCC_TIMEOUT_MS=20000 timeout 240 $TR --master-port 29801 examples/train_vit.py --entry_point 7 --profile_freq 6 --steps 14 --batch 128 > gpurun_out/c9_vit_$N.log 2>&1; grep -E "step (1|5|6|7|13) |reconstruct|Traceback|Error" gpurun_out/c9_vit_$N.log | head -10; lap vit
 S=$((N-1)); [ $N -ge 8 ] && S="$((N-2)),$((N-1))"
 ADAPCC_TIMEOUT_MS=20000 timeout 200 $TR --master-port 29802 examples/train_moe.py --steps 14 --stragglers $S --straggle_ms 100 --relay_mode forward --algo tree > gpurun_out/c9_moe_relay_$N.log 2>&1; grep -E "rank 0\] step (1|5|13)|relay_steps|Error|Traceback" gpurun_out/c9_moe_relay_$N.log | cut -c1-160 | tail -12

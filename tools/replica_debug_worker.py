@@ -21,7 +21,7 @@ cfg = GPT2Config()
 torch.manual_seed(1234)
 model = GPT2DoubleHeads(cfg).to(dev)
 comm = NativeComm(unique_name("rep"), rank, world, local, staging_bytes=64 << 20, heap_bytes=(model.num_parameters() * 2 >> 20 << 20) + (128 << 20))
-eng = FlatDataParallel(model, comm, world_size=world, rank=rank, lr=6.25e-5, max_norm=1.0)
+eng = FlatDataParallel(model, comm, world_size=world, rank=rank, lr=6.25e-5, max_norm=1.0, zero1=False)
 batch = synthetic_batch(4, 2, 1024, cfg.vocab_size, device=dev, seed=1000 * rank)
 names = [(n, o, p.numel()) for (n, p), o in zip(model.named_parameters(), eng._offsets)]
 

@@ -28,7 +28,8 @@ def main() -> int:
     ap.add_argument("--out", default="gpurun_out/ddp_timeline.md")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--impl", default="adapcc", choices=["adapcc", "nccl"])
-    ap.add_argument("--zero1", action="store_true")
+    ap.add_argument("--zero1", action="store_true", help="(the default at N > 1)")
+    ap.add_argument("--no_zero1", action="store_true", help="replicated optimizer + all-reduce")
     ap.add_argument("--bucket_mb", type=float, default=32.0)
     a = ap.parse_args()
 
@@ -58,7 +59,7 @@ def main() -> int:
         args = SimpleNamespace(port=5100, strategy_file=os.path.join(work, "strategy", f"prof_{world}.xml"),
                                logical_graph=os.path.join(work, "topology", f"logical_graph_{world}.xml"),
                                entry_point=-1, parallel_degree=min(4, world), profile_freq=500, work_dir=work,
-                               relay_control=False, algo="auto", heap_mb=((2 if a.zero1 else 1) * n_params * 2 >> 20) + 64,
+                               relay_control=False, algo="auto", heap_mb=((1 if a.no_zero1 else 2) * n_params * 2 >> 20) + 64,
                                staging_mb=64, backend="nccl")
         AdapCC.init(args, local, rank, world)
         AdapCC.setup(ALLREDUCE)
@@ -67,7 +68,7 @@ def main() -> int:
         def comm_fn(seg):
             dist.all_reduce(seg, op=dist.ReduceOp.AVG)
     eng = FlatDataParallel(model, comm, world_size=world, rank=rank, bucket_mb=a.bucket_mb, lr=6.25e-5, max_norm=1.0,
-                           comm_fn=comm_fn, zero1=(a.zero1 and comm is not None) or None)
+                           comm_fn=comm_fn, zero1=False if a.no_zero1 else None)
     batch = synthetic_batch(4, 2, 1024, cfg.vocab_size, device=dev, seed=rank)
     eng.capture(batch, warmup=2)
     for _ in range(5):
@@ -76,7 +77,7 @@ def main() -> int:
     if world > 1:
         dist.barrier()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for _ in range(a.steps):
+        for _ in range(a.steps + 1):          # the first profiled step absorbs CUPTI's start-up skew between the ranks
             eng._graph.replay()
         torch.cuda.synchronize()
     ks = []
@@ -97,11 +98,14 @@ def main() -> int:
     step_begin = 0
     summary = []
     for si, opt_i in enumerate(starts):
+        skip_first = si == 0 and len(starts) > 1
         last = opt_i
         while last + 1 < len(ks) and in_optimizer(ks[last + 1]):
             last += 1
         seg = ks[step_begin:last + 1]
         step_begin = last + 1
+        if skip_first:
+            continue
         t0 = seg[0][0]
         comm_k = [k for k in seg if COMM_PAT.search(k[2]) and "adamw" not in k[2] and k[0] < ks[opt_i][0]]
         comp_k = [k for k in seg if not COMM_PAT.search(k[2])]
