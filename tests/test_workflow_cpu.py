@@ -54,8 +54,19 @@ def _worker(rank, world, port, coord_port, tmp, q):
             ok &= os.path.exists(os.path.join(tmp, "topology", "topo_detect_0.xml"))
             ok &= os.path.exists(args.logical_graph) and os.path.exists(args.strategy_file)
             ok &= all(os.path.exists(os.path.join(tmp, "topology", f"topo_profile_{r}")) for r in range(world))
-            Strategy.from_file(args.strategy_file).validate(world)
+            st = Strategy.from_file(args.strategy_file)
+            st.validate(world)
+            # the synthesizer's per-message algorithm plan travels inside the strategy XML ...
+            from adapcc_b200.synth.plan import AlgoPlan
+            plan = AlgoPlan.from_attrs(st.attrs)
+            ok &= plan is not None and len(plan.bands) >= 1 and plan.bands[-1][0] >= 1 << 60
+            # ... and its thresholds in tunables.json
+            import json as _json
+            tun = _json.load(open(os.path.join(tmp, "topology", "tunables.json")))
+            ok &= "bands" in tun and "one_shot_max_bytes" in tun and "ll_max_bytes" in tun
         comm = AdapCC.communicator
+        ok &= getattr(comm, "plan", None) is not None                 # every rank loaded the same bands
+        ok &= comm._resolve_algo(1 << 20, torch.float32, list(range(world))) in ("auto", "tree", "one_shot", "two_shot", "nvls", "ll")
         t = torch.full((1000,), float(rank + 1))
         comm.all_reduce(t, 1000)
         ok &= bool(torch.allclose(t, torch.full((1000,), world * (world + 1) / 2)))
