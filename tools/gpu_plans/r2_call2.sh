@@ -6,7 +6,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 
 timeout 300 python -m pytest tests/test_gpu_ops.py -q -x > gpurun_out/c2_pytest_ops.log 2>&1; tail -4 gpurun_out/c2_pytest_ops.log
 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/c2_bench1.json 2> gpurun_out/c2_bench1.err; tail -1 gpurun_out/c2_bench1.json | cut -c1-260; tail -2 gpurun_out/c2_bench1.err
 ADAPCC_FUSED_EMBED=0 timeout 200 python bench.py --steps 20 --warmup 5 > gpurun_out/c2_bench1_noembed.json 2> gpurun_out/c2_bench1_noembed.err; tail -1 gpurun_out/c2_bench1_noembed.json | cut -c1-200
-ADAPCC_LL=1 ADAPCC_EXPERIMENTAL=1 ADAPCC_TIMEOUT_MS=15000 timeout 500 $TR --master-port 29601 tests/gpu_collectives_worker.py --quick --sweep --out gpurun_out/c2_worker.json > gpurun_out/c2_worker.log 2>&1
+ADAPCC_TIMEOUT_MS=15000 timeout 500 $TR --master-port 29601 tests/gpu_collectives_worker.py --quick --sweep --out gpurun_out/c2_worker.json > gpurun_out/c2_worker.log 2>&1
 grep -E "FAIL|failures|checks per rank|Error|error" gpurun_out/c2_worker.log | head -20; grep -E "\[sweep\]|\[prims\]" gpurun_out/c2_worker.log | cut -c1-420 | head -24
 ADAPCC_TIMEOUT_MS=15000 timeout 300 $TR --master-port 29604 tests/gpu_workflow_worker.py > gpurun_out/c2_workflow.log 2>&1; grep -E "workflow\]|relay_steps|Error|Traceback" gpurun_out/c2_workflow.log | tail -6
 ADAPCC_TIMEOUT_MS=15000 timeout 300 $TR --master-port 29602 tests/gpu_zero1_worker.py > gpurun_out/c2_zero1.log 2>&1; grep -E "zero1|Error|Traceback" gpurun_out/c2_zero1.log | tail -8
