@@ -75,7 +75,7 @@ class AdapCC:
 
     @classmethod
     def setup(cls, prim):
-        """Build the data-plane context for ``prim`` (ALLREDUCE / REDUCE / BOARDCAST / ALLTOALL): symmetric buffers,
+        """Build the data-plane context for ``prim`` (ALLREDUCE / REDUCE / BOARDCAST / ALLGATHER / ALLTOALL / REDUCESCATTER): symmetric buffers,
         strategy tables, coordinator + controller when relay control is on (reference: /root/reference/adapcc.py:44-46)."""
         cls._comm().init_threads(prim)
 
@@ -104,6 +104,19 @@ class AdapCC:
         from .parallel.alltoall import all_to_all_single
 
         return all_to_all_single(cls._comm(), tensor, size)
+
+    @classmethod
+    def reducescatter(cls, tensor, size=None, chunk_bytes=None, op="sum"):
+        """In-place reduce-scatter (primitive id 5; the reference only declares the id, /root/reference/commu.py:19-26):
+        returns ``(lo, hi)``, the element range of ``tensor`` holding this rank's reduced shard. GPU: the direct reduce
+        kernel with root = self over peer memory (half the bytes of an all-reduce)."""
+        return cls._comm().reduce_scatter(tensor, size, op)
+
+    @classmethod
+    def allgather(cls, tensor, size=None, chunk_bytes=None):
+        """In-place all-gather (primitive id 3), the inverse of :meth:`reducescatter`: every rank contributes its shard
+        of ``tensor`` and ends up with all of them. GPU: one multicast-store broadcast per shard."""
+        return cls._comm().all_gather(tensor, size)
 
     @classmethod
     def reconstruct_topology(cls, args, prim):

@@ -40,7 +40,7 @@ from .synth import LinkModel, Synthesizer, crossover_bytes
 __all__ = ["CudaCommu", "ALLREDUCE", "REDUCE", "BOARDCAST", "ALLGATHER", "ALLTOALL", "REDUCESCATTER", "DETECT",
            "PROFILE"]
 
-_DATA_PRIMS = (ALLREDUCE, REDUCE, BOARDCAST)
+_DATA_PRIMS = (ALLREDUCE, REDUCE, BOARDCAST, ALLGATHER, ALLTOALL, REDUCESCATTER)
 
 
 def _arg(args, name, default):
@@ -417,7 +417,7 @@ class CudaCommu:
                 self._log("transmission context setup time=%6.2f(ms)" % ((time.time() - t0) * 1e3))
             self._open_prims.add(prim)
         else:
-            raise NotImplementedError(f"primitive {prim} is not implemented (the reference implements 0,1,2,6,7)")
+            raise NotImplementedError(f"primitive {prim} is not a known primitive id (0-7, see adapcc_b200/constants.py)")
         self.init_count += 1
 
     def exit_threads(self, prim):
@@ -785,6 +785,20 @@ class CudaCommu:
         return self._collective(BOARDCAST, buffer, size, chunk_bytes, active_gpus, "sum", root)
 
     broadcast = boardcast
+
+    def reduce_scatter(self, buffer, size=None, op="sum"):
+        """In-place reduce-scatter over all ranks; returns ``(lo, hi)``: the element range of ``buffer[:size]`` that holds
+        this rank's reduced shard afterwards (16-byte packs dealt out contiguously, ``parallel.engine.shard_of``)."""
+        from .parallel.shards import reduce_scatter
+
+        return reduce_scatter(self, buffer, size, op)
+
+    def all_gather(self, buffer, size=None):
+        """In-place all-gather, the inverse of :meth:`reduce_scatter`: rank r's shard of ``buffer[:size]`` is valid on
+        entry, the whole range on exit."""
+        from .parallel.shards import all_gather
+
+        return all_gather(self, buffer, size)
 
     def synchronize(self):
         """Wait for the data plane and raise if a device-side wait timed out."""

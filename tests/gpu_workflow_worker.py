@@ -51,6 +51,16 @@ def main():
     comm.boardcast(t, 5000)
     comm.synchronize()
     ok &= bool((t == 0).all())
+    # reduce-scatter / all-gather through the public API (native reduce with root = self + per-shard broadcasts)
+    n = 100_003
+    t = torch.arange(n, dtype=torch.float32, device=dev) % 97 * (rank + 1)
+    full = torch.arange(n, dtype=torch.float32, device=dev) % 97 * (world * (world + 1) / 2)
+    lo, hi = comm.reduce_scatter(t)
+    comm.synchronize()
+    ok &= 0 <= lo < hi <= n and bool(torch.equal(t[lo:hi], full[lo:hi]))
+    comm.all_gather(t)
+    comm.synchronize()
+    ok &= bool(torch.equal(t, full))
     # DDP + hook, buckets in the symmetric heap, a straggler from step 2 on
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(512, 2048), torch.nn.ReLU(), torch.nn.Linear(2048, 512)).to(dev)

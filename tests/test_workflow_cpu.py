@@ -73,6 +73,24 @@ def _worker(rank, world, port, coord_port, tmp, q):
         a2a = AdapCC.alltoall(torch.arange(world * 3, dtype=torch.float32) + 100 * rank)
         want = torch.cat([torch.arange(rank * 3, rank * 3 + 3, dtype=torch.float32) + 100 * src for src in range(world)])
         ok &= bool(torch.equal(a2a, want))
+        # reduce-scatter / all-gather (ids 5 / 3: declared but never implemented by the reference): in place, shard layout
+        # of the direct kernels; reduce-scatter followed by all-gather is an all-reduce
+        from adapcc_b200 import ALLGATHER, REDUCESCATTER
+        AdapCC.setup(REDUCESCATTER)
+        AdapCC.setup(ALLGATHER)
+        n = 1003                                                     # odd tail: the last shard is short
+        x = torch.arange(n, dtype=torch.float32) * (rank + 1)
+        lo, hi = AdapCC.reducescatter(x)
+        full = torch.arange(n, dtype=torch.float32) * (world * (world + 1) / 2)
+        ok &= 0 <= lo < hi <= n and bool(torch.equal(x[lo:hi], full[lo:hi]))
+        spans = [None] * world
+        dist.all_gather_object(spans, (lo, hi))
+        ok &= sorted(spans)[0][0] == 0 and sorted(spans)[-1][1] == n and all(a[1] == b[0] for a, b in zip(sorted(spans), sorted(spans)[1:]))
+        AdapCC.allgather(x)
+        ok &= bool(torch.equal(x, full))
+        y = torch.full((64,), float(rank))
+        lo, hi = AdapCC.reducescatter(y, op="avg")
+        ok &= bool(torch.allclose(y[lo:hi], torch.full((hi - lo,), (world - 1) / 2)))
         AdapCC.reconstruct_topology(args, ALLREDUCE)   # clear + init + setup again (re-entrant)
         comm = AdapCC.communicator
         t = torch.full((77,), 2.0)
