@@ -109,7 +109,7 @@ def get_dataset(tokenizer: DialogTokenizer, dataset_path: str = "", dataset_cach
     """Tokenized dataset: from ``dataset_cache`` if it exists, else from the JSON file at ``dataset_path``, else a
     synthetic one (``synthetic`` = kwargs of :func:`synthetic_personachat`). Counterpart of the reference's
     ``get_dataset`` (utils.py:34-56) minus the S3 download."""
-    cache = f"{dataset_cache}_{type(tokenizer).__name__}_{tokenizer.base_vocab}" if dataset_cache else ""
+    cache = f"{dataset_cache}_{type(tokenizer).__name__}_{tokenizer.fingerprint()}" if dataset_cache else ""
     if cache and os.path.isfile(cache):
         return torch.load(cache, weights_only=False)
     if dataset_path:
@@ -119,8 +119,9 @@ def get_dataset(tokenizer: DialogTokenizer, dataset_path: str = "", dataset_cach
         raw = synthetic_personachat(**(synthetic or {}))
     data = _tokenize(raw, tokenizer)
     if cache:
-        torch.save(data, cache + ".tmp")
-        os.replace(cache + ".tmp", cache)
+        tmp = f"{cache}.{os.getpid()}.tmp"              # every rank may get here at once: private file, atomic publish
+        torch.save(data, tmp)
+        os.replace(tmp, cache)
     return data
 
 

@@ -73,6 +73,16 @@ class DialogTokenizer:
             return self.special.get(tokens, self.index.get(tokens))
         return [self.convert_tokens_to_ids(t) for t in tokens]
 
+    def fingerprint(self) -> str:
+        """Short hash of the vocabulary (cache keys: a tokenized dataset is only valid for the tokenizer that made it)."""
+        import hashlib
+
+        h = hashlib.sha1()
+        for s in self.symbols:
+            h.update(s.encode("utf-8") + b"\0")
+        h.update(str(self.model_vocab).encode())
+        return h.hexdigest()[:12]
+
     # ------------------------------------------------------------------ training
     @classmethod
     def train(cls, corpus: Iterable[str], vocab_size: int = 2048, model_vocab: Optional[int] = None,
