@@ -1,4 +1,4 @@
-// Sharded optimizer step fused with its collective (ZeRO-1 over NVSwitch) — opt-in, compiled only so far.
+// Sharded optimizer step fused with its collective (ZeRO-1 over NVSwitch) — the engine's default at N > 1 (parity-tested).
 //
 // Data-parallel training ends every step with: all-reduce(grads) -> every rank runs the SAME AdamW over ALL
 // parameters (the reference: DDP + optimizer.step per rank, /root/reference/train_ddp.py:37-54). On one NVSwitch

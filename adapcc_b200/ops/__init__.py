@@ -86,8 +86,8 @@ def zero_adamw_bcast_(comm, param_shard: torch.Tensor, grad_shard: torch.Tensor,
     """ZeRO-1 step for one shard (csrc/zero.cu): AdamW on this rank's slice of the (symmetric-heap) parameter
     buffer; the updated bf16 parameters are written through the heap's multicast alias (``multimem.st``: the switch
     replicates them into every rank's copy) or, without multicast, stored into every peer's buffer. ``param_shard``
-    must be a view inside ``comm``'s symmetric heap; master / m / v are the shard's fp32 state. Opt-in path, first
-    GPU run pending."""
+    must be a view inside ``comm``'s symmetric heap; master / m / v are the shard's fp32 state. The engine's default at
+    N > 1 (``tests/gpu_zero1_worker.py``: parity with the replicated optimizer at 2 and 8 GPUs)."""
     n = param_shard.numel()
     if n == 0:
         return

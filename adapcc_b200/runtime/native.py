@@ -298,7 +298,7 @@ class NativeComm:
         """In-place reduce-scatter over all ranks: afterwards elements ``[lo, hi)`` of ``tensor`` (the returned
         range, this rank's slice under the direct kernels' partition) hold the reduction; the rest of the tensor
         is unspecified. It is the direct reduce kernel with root = self, so it moves half the bytes of an
-        all-reduce. (Used by the engine's sharded-optimizer mode; first GPU run pending.)"""
+        all-reduce. (Used by the engine's sharded-optimizer mode and ``AdapCC.reducescatter``.)"""
         from ..parallel.engine import shard_of
 
         self.reduce(tensor, root=self.rank, op=op, algo=algo, stream=stream)
