@@ -377,3 +377,20 @@ def test_hook_training_matches_stock_ddp_on_cpu(tmp_path):
     assert len(rows) == 3, r.stdout
     for _, diff, a0, a1 in rows:
         assert float(diff) < 1e-5 and float(a0) > 0.9 and abs(float(a0) - float(a1)) < 1e-6
+
+
+def test_synthetic_ddp_benchmark_on_cpu(tmp_path):
+    """adapcc_b200/bench/synthetic_ddp.py (the reference's Horovod synthetic img/s benchmark, nccl-perf/pytorch_synthetic.py)
+    on 2 gloo ranks through the communicator's hook, with the Horovod script's ``--fp16-allreduce`` switch."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""), CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), "-m", "adapcc_b200.bench.synthetic_ddp", "--backend", "gloo", "--model", "resnet18",
+           "--image_size", "32", "--num-classes", "10", "--batch-size", "8", "--num-warmup-batches", "1",
+           "--num-batches-per-iter", "2", "--num-iters", "2", "--fp16-allreduce"]
+    import subprocess
+    r = subprocess.run(cmd, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-800:] + r.stderr[-2500:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("Img/sec per GPU:")]
+    assert len(line) == 1 and "total on 2 GPU(s)" in line[0] and "wire=float16" in line[0]
+    assert float(line[0].split(":")[1].split()[0]) > 0
