@@ -83,6 +83,11 @@ class CudaCommu:
         self.reduce_op = _arg(args, "reduce_op", "avg")       # DDP hook; primitives default to "sum"
         self.relay_mode = RELAY_BYPASS if str(_arg(args, "relay_mode", "forward")) in ("bypass", "1") else RELAY_FORWARD
         self.is_bsp = bool(_arg(args, "bsp", True))
+        if not self.is_bsp and world_rank == 0:
+            # the reference's non-BSP join (a late rank re-enters mid-step, /root/reference/commu.py:427-431) marks the
+            # rank active in ITS process only, so the ranks disagree on the active set; relays stay relays for the step here
+            print("[adapcc] bsp=False: the non-BSP late join is not implemented; late ranks relay for the whole step (BSP)",
+                  flush=True)
         self.relay_control = bool(_arg(args, "relay_control", True)) and world_size > 1
         self.staging_bytes = int(_arg(args, "staging_mb", os.environ.get("ADAPCC_STAGING_MB", 256))) << 20
         self.heap_bytes = int(_arg(args, "heap_mb", os.environ.get("ADAPCC_HEAP_MB", 0))) << 20
