@@ -264,8 +264,12 @@ class FlatDataParallel:
         out = self.model(**batch)
         loss = out[0] if isinstance(out, (tuple, list)) else out
         loss.backward()
+        for b in self.buckets:
+            if b.pending > 0:                         # parameters that got no gradient this step (unused branch):
+                b.pending = 0                         # their zeros still travel, or the bucket's other gradients
+                self._launch_bucket(b)                # would stay un-averaged (same parameters on every rank, as in DDP)
         cur = torch.cuda.current_stream(self.device)
-        if self._forked:                              # join the collective stream (also under capture)
+        if self._forked:                            # join the collective stream (also under capture)
             cur.wait_stream(self.comm_stream)
         incr_(self.step_t)
         if self.zero1:
