@@ -19,12 +19,12 @@ import json
 import os
 import random
 from dataclasses import dataclass
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
 import torch
 
-from .tokenizer import SPECIAL_TOKENS, DialogTokenizer
+from .tokenizer import DialogTokenizer
 
 MODEL_INPUTS = ("input_ids", "mc_token_ids", "lm_labels", "mc_labels", "token_type_ids")
 IGNORE = -100

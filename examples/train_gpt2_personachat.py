@@ -24,7 +24,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from adapcc_b200 import ALLREDUCE  # noqa: E402
 from adapcc_b200.adapcc import AdapCC  # noqa: E402
-from adapcc_b200.data import (DialogTokenizer, PinnedPrefetcher, corpus_of, get_data_loaders, get_dataset,  # noqa: E402
+from adapcc_b200.data import (DialogTokenizer, PinnedPrefetcher, corpus_of, get_data_loaders,  # noqa: E402
                               synthetic_personachat)
 from adapcc_b200.eval import evaluate_tensors, pack_checkpoint  # noqa: E402
 from adapcc_b200.models.gpt2 import GPT2Config, GPT2DoubleHeads  # noqa: E402

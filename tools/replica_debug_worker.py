@@ -2,7 +2,6 @@
 parameters / gradients differ between the ranks?"""
 import os
 import sys
-from types import SimpleNamespace
 
 import torch
 import torch.distributed as dist
