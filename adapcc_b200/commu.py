@@ -637,7 +637,7 @@ class CudaCommu:
             return "auto"
         import torch
 
-        esize = torch.empty((), dtype=getattr(torch, wire) if isinstance(wire, str) else dtype).element_size()
+        esize = (getattr(torch, wire) if isinstance(wire, str) else dtype).itemsize      # per hook call: no tensor allocation
         n = self.native
         zero_copy = bool(tensor is not None and n is not None and wire is None and n.in_heap(tensor))
         return plan.pick(int(numel) * esize, zero_copy=zero_copy, all_active=len(active) == self.world_size,
