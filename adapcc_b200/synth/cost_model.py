@@ -56,6 +56,12 @@ class LinkModel:
 # One hop of the strategy-tree kernel costs more than a link latency: the parent polls the child's flag over NVLink
 # (a round trip), then pulls; measured 44 us for a one-chunk 6-hop all-reduce on 8xB200 -> ~3.5 alpha per hop.
 TREE_HOP_ALPHAS = 3.5
+# The FIRST chunk of a lane crosses every hop at the rate of ONE CTA pulling over NVLink (512 threads x 16-byte loads,
+# latency-bound), not at the link rate; later chunks overlap across the kernel's lanes and stream at a fraction of the link
+# rate (flag polling and the staging passes share the ports). Both fitted on the 8xB200 measurements of the kernel with
+# 3 trees (round 2: profiles/raw/sweep_8xB200_r2.json) and 4 trees (round 1): every size 64 KB - 1 GiB within +-32 %.
+TREE_LANE_GBS = 30.0
+TREE_STREAM_EFF = 0.72
 
 
 def tree_time(tree: Tree, lm: LinkModel, slice_bytes: float, chunk_bytes: float, bcast: bool = True,
@@ -70,6 +76,7 @@ def tree_time(tree: Tree, lm: LinkModel, slice_bytes: float, chunk_bytes: float,
     chunk = max(16.0, min(chunk_bytes, slice_bytes))
     n_chunks = max(1.0, slice_bytes / chunk)
     step_max = 0.0
+    lane_beta = 1.0 / (TREE_LANE_GBS * GB)
 
     def step(x: int, lat: float = 1.0) -> float:
         kids = tree.kids(x)
@@ -84,22 +91,24 @@ def tree_time(tree: Tree, lm: LinkModel, slice_bytes: float, chunk_bytes: float,
         kids = tree.kids(x)
         if not kids:
             return 0.0
-        return step(x, TREE_HOP_ALPHAS) + max(fill(c) for c in kids)
+        slow = max(1.0, max(lm.beta(c, x) for c in kids) / lane_beta)        # a slower-than-a-lane link bounds the hop
+        return (TREE_HOP_ALPHAS * max(lm.alpha(c, x) for c in kids) + len(kids) * chunk * lane_beta * slow
+                + max(fill(c) for c in kids))
 
     for x in tree.nodes:
         step_max = max(step_max, step(x))
-    t = fill(tree.root) + (n_chunks - 1) * step_max
+    t = fill(tree.root) + (n_chunks - 1) * step_max / TREE_STREAM_EFF
     if bcast:
         # same edges backwards; a child's pull is one flow on its own ingress
         def bfill(x: int) -> float:
             kids = tree.kids(x)
             if not kids:
                 return 0.0
-            return max(TREE_HOP_ALPHAS * lm.alpha(x, c) + chunk * lm.beta(x, c) + bfill(c) for c in kids)
+            return max(TREE_HOP_ALPHAS * lm.alpha(x, c) + chunk * max(lane_beta, lm.beta(x, c)) + bfill(c) for c in kids)
         egress = max((len(tree.kids(x)) for x in tree.nodes), default=1)
         bstep = max((lm.alpha(x, c) + chunk * lm.beta(x, c) * max(1, len(tree.kids(x)))
                      for x in tree.nodes for c in tree.kids(x)), default=0.0)
-        t = max(t, fill(tree.root)) + bfill(tree.root) + max(0.0, (n_chunks - 1) * (bstep - step_max))
+        t = max(t, fill(tree.root)) + bfill(tree.root) + max(0.0, (n_chunks - 1) * (bstep - step_max) / TREE_STREAM_EFF)
         _ = egress
     return t
 
