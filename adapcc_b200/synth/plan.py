@@ -21,6 +21,9 @@ from .cost_model import LAUNCH_US, LinkModel, direct_times, strategy_time
 
 INF_BYTES = 1 << 62
 LL_MAX_BYTES = 32768
+# the one-shot kernel has been measured up to 4 MB (where it stops winning on 8 GPUs and ties the two-shot on 2); the model
+# would extrapolate it to any size on 2 ranks (same bytes as a two-shot, one staging pass fewer) — not without a measurement
+ONE_SHOT_MAX_BYTES = 4 << 20
 ALGOS = ("ll", "one_shot", "two_shot", "nvls", "tree")
 
 
@@ -107,7 +110,7 @@ def build_plan(lm: LinkModel, strategy: Optional[Strategy] = None, chunk_bytes: 
         winners = []
         for nb in sizes:
             t = direct_times(lm, float(nb), None, nvls, nvls_bw_gbs or None, zero_copy=zc)
-            if zc:
+            if zc or nb > ONE_SHOT_MAX_BYTES:
                 t.pop("one_shot", None)
             if ll and nb <= LL_MAX_BYTES:
                 t["ll"] = ll_time(lm, float(nb))
