@@ -575,7 +575,12 @@ class CudaCommu:
         self.synthesizer.set_bandwidth_graph(bw_graph)
         self.chunk_bytes = self.synthesizer.generate_strategy("reduce")
         self.link_model = LinkModel(lc_graph, bw_graph)
-        if self.coordinator is not None and self.accumulated_bw > 0:
+        # The rent/buy rule keeps the reference's constants (100*8/1024 GB per step over 50 GB/s x world,
+        # /root/reference/proto/rpc_server.py:41-42 — the reference computes the profiled sum too, commu.py:266-269, and
+        # never hands it over): with the profiled NVSwitch bandwidth a collective costs so little that the leader would stop
+        # waiting after ~0.2 ms and ordinary arrival jitter would turn healthy ranks into relays. Opt in with
+        # args.rent_from_profile (in-process coordinator only).
+        if self.coordinator is not None and self.accumulated_bw > 0 and bool(_arg(self.args, "rent_from_profile", False)):
             self.coordinator.set_traffic(self.coordinator.accumulated_size, self.accumulated_bw)
         ext = getattr(self, "_profile_ext", {"nvls": []})
         nvls = max(ext.get("nvls", [0.0]) or [0.0])
