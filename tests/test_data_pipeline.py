@@ -11,6 +11,18 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+
+def _free_ports(n):
+    import socket
+
+    socks = [socket.socket() for _ in range(n)]
+    for s in socks:
+        s.bind(("127.0.0.1", 0))
+    ports = [s.getsockname()[1] for s in socks]
+    for s in socks:
+        s.close()
+    return ports
+
 from adapcc_b200.data import (DialogTokenizer, PinnedPrefetcher, build_input_from_segments, build_tensors,  # noqa: E402
                               corpus_of, get_data_loaders, get_dataset, synthetic_personachat)
 from adapcc_b200.eval import f1_score, normalize_answer, top_filtering  # noqa: E402
@@ -133,10 +145,12 @@ def test_train_evaluate_interact_end_to_end(tmp_path):
     """examples/train_gpt2_personachat.py on 2 gloo ranks (tokenizer built by rank 0, distributed loaders, DDP + the
     communicator's hook, linear lr decay, validation all-reduced, checkpoint), then the evaluation and chat scripts."""
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    mport, cport, sport = _free_ports(3)
+    env["ADAPCC_COORD_PORT"] = str(cport)
     train = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-             "--master-port", "29671", os.path.join(ROOT, "examples", "train_gpt2_personachat.py"), "--backend", "gloo", "--tiny",
+             "--master-port", str(mport), os.path.join(ROOT, "examples", "train_gpt2_personachat.py"), "--backend", "gloo", "--tiny",
              "--n_epochs", "2", "--synthetic_dialogs", "24", "--lr", "3e-3", "--eval_before_start", "--checkpoint", "ck.pt",
-             "--port", "5391"]
+             "--port", str(sport)]
     r = subprocess.run(train, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
     vals = [float(line.split("nll ")[1].split()[0]) for line in r.stdout.splitlines() if line.startswith("validation")]
@@ -163,10 +177,12 @@ def test_accuracy_benchmark_and_log_processors(tmp_path):
     all-reduced over an exact partition, the GNS probe prints, checkpoints resume; tools/process_log.py extracts the
     Acc@1 / gns series the reference keeps as accuracy_*.txt / gns-split-all.txt."""
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    mport, cport, sport = _free_ports(3)
+    env["ADAPCC_COORD_PORT"] = str(cport)
     base = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-            "--master-port", "29673", os.path.join(ROOT, "examples", "accuracy_benchmark.py"), "--dummy", "--backend", "gloo",
+            "--master-port", str(mport), os.path.join(ROOT, "examples", "accuracy_benchmark.py"), "--dummy", "--backend", "gloo",
             "-a", "resnet18", "--image_size", "32", "--classes", "10", "--dummy_size", "768", "-b", "16", "--lr", "0.05",
-            "--gns_freq", "8", "-p", "4", "--port", "5395", "--seed", "0"]
+            "--gns_freq", "8", "-p", "4", "--port", str(sport), "--seed", "0"]
     r = subprocess.run(base + ["--epochs", "1"], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
     (tmp_path / "run.out").write_text(r.stdout)
