@@ -21,8 +21,13 @@ def test_reference_arm_contract_on_cpu():
         assert r.returncode == 0, r.stderr
         rec = json.loads(r.stdout.strip().splitlines()[-1])
         assert rec["impl"] == "reference" and "unavailable" in rec and len(rec["unavailable"]) > 20
+    import socket
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     r = subprocess.run(base + ["--tiny", "--allow_cpu", "--seq", "32"], capture_output=True, text=True, timeout=600,
-                       env=dict(os.environ, CUDA_VISIBLE_DEVICES="", MASTER_PORT="29577"))
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES="", MASTER_PORT=str(port)))
     assert r.returncode == 0, r.stderr[-2000:]
     rec = json.loads(r.stdout.strip().splitlines()[-1])
     assert rec["impl"] == "reference" and rec["metric"] == "gpt2_small_ddp_train_tokens_per_sec" and rec["value"] > 0
