@@ -19,7 +19,8 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 SPECIAL_TOKENS = ("<bos>", "<eos>", "<speaker1>", "<speaker2>", "<pad>")
 
 # words keep their leading blank (GPT-2's convention), digits and punctuation are split off
-_PRETOKEN = re.compile(r"'s|'t|'re|'ve|'m|'ll|'d| ?[^\W\d_]+| ?\d+| ?[^\s\w]+|\s+(?!\S)|\s+", re.UNICODE)
+# (the underscore is a "word" character for `re` but neither a letter nor a digit: it belongs to the punctuation class)
+_PRETOKEN = re.compile(r"'s|'t|'re|'ve|'m|'ll|'d| ?[^\W\d_]+| ?\d+| ?(?:[^\s\w]|_)+|\s+(?!\S)|\s+", re.UNICODE)
 
 
 def _byte_symbols() -> Tuple[Dict[int, str], Dict[str, int]]:

@@ -207,3 +207,41 @@ def test_accuracy_benchmark_and_log_processors(tmp_path):
     ev = subprocess.run(base + ["--evaluate", "--resume", "checkpoint.pth.tar", "--bfp16"], cwd=tmp_path, env=env,
                         capture_output=True, text=True, timeout=900)
     assert ev.returncode == 0 and " *   Acc@1" in ev.stdout and "Epoch:" not in ev.stdout, ev.stderr[-2000:]
+
+
+def test_tokenizer_and_layout_properties(tok):
+    """Property tests: any text survives encode → decode; any (persona, history, reply) yields a well-formed input."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.text(max_size=60))
+    def roundtrip(text):
+        ids = tok.encode(text)
+        assert all(0 <= i < tok.base_vocab for i in ids)
+        assert tok.decode(ids) == text.encode("utf-8", errors="replace").decode("utf-8", errors="replace")
+
+    roundtrip()
+    seg = st.lists(st.integers(0, tok.base_vocab - 1), min_size=1, max_size=12)
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(seg, min_size=1, max_size=4), st.lists(seg, min_size=0, max_size=5), seg, st.booleans(), st.booleans(),
+           st.one_of(st.none(), st.integers(8, 64)))
+    def layout(persona, history, reply, lm, eos, max_len):
+        bos, eos_id, s1, s2, _ = tok.special_ids
+        inst = build_input_from_segments(persona, history, reply, tok, lm_labels=lm, with_eos=eos, max_len=max_len)
+        n = len(inst.input_ids)
+        assert n == len(inst.token_type_ids) == len(inst.lm_labels) and inst.mc_token_id == n - 1
+        if max_len is not None:
+            assert n <= max_len
+        assert set(inst.token_type_ids) <= {s1, s2}
+        tail = list(reply) + ([eos_id] if eos else [])
+        assert inst.input_ids[-min(n, len(tail)):] == tail[-min(n, len(tail)):]           # the reply always survives, at the end
+        scored = [x for x in inst.lm_labels if x != -100]
+        if lm:
+            assert scored == tail[-len(scored):] and len(scored) <= len(tail)            # labels = (a suffix of) the reply only
+        else:
+            assert not scored
+        if max_len is None:
+            assert inst.input_ids[0] == bos and inst.input_ids.count(bos) == 1
+
+    layout()
