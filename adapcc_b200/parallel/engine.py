@@ -43,7 +43,7 @@ def shard_of(start: int, end: int, rank: int, world: int, elems_per_pack: int) -
     pps = (packs + world - 1) // world
     lo = min(packs, rank * pps) * elems_per_pack
     hi = min(packs, (rank + 1) * pps) * elems_per_pack
-    return start + lo, min(end, start + hi)
+    return min(end, start + lo), min(end, start + hi)       # an empty trailing shard is (end, end), never lo > hi
 
 
 class _GradSink:

@@ -224,3 +224,45 @@ def test_algorithm_plan_bands_follow_the_profile():
     plan2 = build_plan(slow, trees)
     assert plan2.pick(1 << 28, zero_copy=True) == "tree" and plan2.pick(1 << 28) == "tree"
     assert plan2.pick(1 << 10) == "ll"
+
+
+def test_plan_encoding_and_pick_properties():
+    """Bands survive the XML attribute round trip for arbitrary band lists; ``pick`` only returns a runnable variant and
+    ``shard_of`` (the partition the ZeRO-1 engine, reducescatter and the direct kernels share) tiles any message exactly."""
+    from hypothesis import given, settings, strategies as st
+
+    from adapcc_b200.parallel.engine import shard_of
+    from adapcc_b200.synth.plan import ALGOS, INF_BYTES, LL_MAX_BYTES, AlgoPlan
+
+    band = st.lists(st.tuples(st.integers(1, 1 << 40), st.sampled_from(ALGOS)), min_size=1, max_size=6).map(
+        lambda bs: sorted(bs)[:-1] + [(INF_BYTES, sorted(bs)[-1][1])])
+
+    @settings(max_examples=200, deadline=None)
+    @given(band, band, st.integers(1, 1 << 34), st.booleans(), st.booleans(), st.booleans(), st.booleans(), st.booleans())
+    def plan_props(b, bz, nbytes, zc, all_active, nvls, ll, tree):
+        p = AlgoPlan(list(b), list(bz))
+        q = AlgoPlan.from_attrs(p.to_attrs())
+        assert q.bands == p.bands and q.bands_zc == p.bands_zc
+        a = q.pick(nbytes, zero_copy=zc, all_active=all_active, nvls=nvls, ll=ll, tree=tree)
+        assert a in ALGOS + ("auto",)
+        assert not (a == "nvls" and not (nvls and all_active))
+        assert not (a == "ll" and (not (ll and all_active) or nbytes > LL_MAX_BYTES))
+        assert not (a == "tree" and not tree) and not (a == "one_shot" and zc)
+
+    plan_props()
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 1 << 20), st.integers(1, 1 << 22), st.integers(1, 16), st.sampled_from([2, 4, 8]))
+    def shards_tile(start, length, world, elems_per_pack):
+        end = start + length
+        spans = [shard_of(start, end, r, world, elems_per_pack) for r in range(world)]
+        pos = start
+        for lo, hi in spans:
+            assert lo == min(pos, end) or hi == lo            # contiguous, in rank order (trailing shards may be empty)
+            assert start <= lo <= hi <= end
+            if hi > lo:
+                assert lo == pos and (lo - start) % elems_per_pack == 0
+                pos = hi
+        assert pos == end
+
+    shards_tile()
