@@ -35,7 +35,11 @@ class PinnedPrefetcher:
         self.bytes_per_batch = 0
 
     def _slots_for(self, batch: Dict[str, torch.Tensor], k: int):
-        if self._host[k] is None:
+        stale = self._host[k] is not None and any(tuple(self._host[k][n].shape) != tuple(t.shape) or self._host[k][n].dtype != t.dtype
+                                                  for n, t in batch.items())
+        if stale and self._ready[k] is not None:               # a ragged (last) batch: give the slot buffers of its shape
+            self._ready[k].synchronize()
+        if self._host[k] is None or stale:
             self._host[k] = {n: (torch.empty_like(t).pin_memory() if self.cuda else torch.empty_like(t))
                              for n, t in batch.items()}
             self._dev[k] = {n: torch.empty_like(t, device=self.device) for n, t in batch.items()}

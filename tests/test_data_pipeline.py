@@ -245,3 +245,21 @@ def test_tokenizer_and_layout_properties(tok):
             assert inst.input_ids[0] == bos and inst.input_ids.count(bos) == 1
 
     layout()
+
+
+def test_prefetcher_handles_ragged_batches_and_any_depth():
+    """The prefetcher returns exactly the loader's batches for any length / batch size / ring depth, including a shorter
+    last batch (its slot is re-shaped) and an empty loader."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(0, 23), st.integers(1, 7), st.integers(2, 4))
+    def prop(n, bs, depth):
+        data = [{"a": torch.arange(i * 3, (i + 1) * 3), "b": torch.tensor([float(i)])} for i in range(n)]
+        coll = lambda items: {k: torch.stack([x[k] for x in items]) for k in ("a", "b")}          # noqa: E731
+        loader = torch.utils.data.DataLoader(data, batch_size=bs, collate_fn=coll)
+        ref = [b for b in loader]
+        got = [{k: v.clone() for k, v in b.items()} for b in PinnedPrefetcher(loader, "cpu", depth=depth)]
+        assert len(ref) == len(got) and all(torch.equal(r[k], g[k]) for r, g in zip(ref, got) for k in r)
+
+    prop()
