@@ -67,6 +67,14 @@ def main(argv=None) -> int:
     nbytes = a.size * 4
     print(open(a.out).read())
     print(f"world {len(ips)}, {len(s.trees)} trees, chunk {chunk} bytes, report {syn.last_report}")
+    if len(set(ips)) == 1:
+        # the same per-message algorithm plan the workflow writes (commu.py::_synthesis_strategy): size bands per algorithm
+        from .plan import build_plan
+
+        plan = build_plan(lm, s, nvls=len(ips) > 2, ll=len(ips) > 1)
+        s.attrs.update(plan.to_attrs())
+        s.save(a.out, compact=True)
+        print(f"algorithm plan (written into {a.out}): staged [{plan.to_attrs()['bands']}]  heap [{plan.to_attrs()['bands_zc']}]")
     print(f"cost model for {nbytes / 1e6:.1f} MB: trees {strategy_time(s, lm, nbytes, chunk) * 1e6:.1f} us; "
           + ", ".join(f"{k} {v * 1e6:.1f} us" for k, v in direct_times(lm, nbytes).items())
           + ("  (direct algorithms assume one NVSwitch domain)" if len(set(ips)) > 1 else ""))
