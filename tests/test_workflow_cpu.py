@@ -394,3 +394,20 @@ def test_synthetic_ddp_benchmark_on_cpu(tmp_path):
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("Img/sec per GPU:")]
     assert len(line) == 1 and "total on 2 GPU(s)" in line[0] and "wire=float16" in line[0]
     assert float(line[0].split(":")[1].split()[0]) > 0
+
+
+def test_doctor_reports_environment_and_rpc_latency():
+    """python -m adapcc_b200.doctor (pre-flight check: the reference's check_mpi_connect / RPC latency dumps): toolchain,
+    native library, GPUs, a 2-process rendezvous on loopback and the coordinator's gRPC round trip."""
+    import json
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "adapcc_b200.doctor", "--ranks", "2", "--rpc", "100", "--json"], cwd=root,
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    rep = json.loads(r.stdout[r.stdout.index("{"):])
+    assert rep["library"]["built"] and rep["library"]["missing_symbols"] == [] and rep["problems"] == []
+    assert rep["rendezvous"]["ok"] and rep["rendezvous"]["backend"] == "gloo" and rep["rendezvous"]["ranks"] == 2
+    c = rep["coordinator_rpc"]
+    assert c["calls"] == 100 and 0 < c["median_ms"] <= c["p95_ms"] <= c["max_ms"] and c["median_ms"] < 50
