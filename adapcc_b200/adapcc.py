@@ -18,6 +18,10 @@ from .constants import (ALLGATHER, ALLREDUCE, ALLTOALL, BOARDCAST, DETECT, PROFI
 
 
 class AdapCC:
+    """Class-level singleton, the library's public face: ``init → setup(prim) → allreduce / reduce / boardcast /
+    alltoall / reducescatter / allgather → clear``, ``reconstruct_topology`` for on-the-fly re-profiling; state
+    lives in ``AdapCC.communicator`` (/root/reference/adapcc.py:6-76)."""
+
     # meta info since the first registered
     communicator_path = None            # resolved lazily: adapcc_b200/_C/libadapcc.so
     communicator: CudaCommu = None

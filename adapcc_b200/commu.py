@@ -49,6 +49,11 @@ def _arg(args, name, default):
 
 
 class CudaCommu:
+    """The control plane of one rank: workflow stages (DETECT / PROFILE → synthesis → data-plane context), the
+    collectives' Python entry points, the DDP communication hook, the controller thread (heartbeat + relay duty) and
+    the coordinator clients — /root/reference/commu.py:37-435, on VMM symmetric memory and in-kernel NVLink
+    transfers instead of cudaIpc staging threads."""
+
     def __init__(self, args, dylib, local_rank, world_rank, world_size):
         self.args = args
         self.dylib = dylib                      # kept for signature parity; ctypes handle or None

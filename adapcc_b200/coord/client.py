@@ -34,6 +34,9 @@ class _Stub:
 
 
 class Controller(_Stub):
+    """Controller-thread client: one heartbeat per step; the reply is the step's active list and a status (0 = a
+    heartbeat deadline was missed, the list holds the survivors) — /root/reference/proto/rpc_client.py:11-22."""
+
     def send_relay_request(self, step: int, world_rank: int) -> Tuple[List[int], int]:
         if self.local is not None:
             return self.local.controller(step, world_rank)
@@ -43,6 +46,9 @@ class Controller(_Stub):
 
 
 class Hooker(_Stub):
+    """Hook client: called with the first gradient bucket of a step; the reply is the step's active list (a late caller
+    learns that it relays) — /root/reference/proto/rpc_client.py:24-35."""
+
     def send_ready_request(self, step: int, world_rank: int) -> List[int]:
         if self.local is not None:
             return self.local.hook(step, world_rank)

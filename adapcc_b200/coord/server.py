@@ -40,6 +40,12 @@ class _Step:
 
 
 class Coordinator:
+    """Per-step negotiation service hosted by rank 0: ``hook`` collects the ranks whose first bucket is ready and
+    closes the set with the reference's rent-or-buy (ski-rental) rule or after ``relay_threshold``; ``controller``
+    is the heartbeat — all alive ranks must report within ``fault_tolerant_time`` or the missing ones are declared
+    dead for the rest of the job. One lock + condition variable, per-step state created lazily and pruned
+    (/root/reference/proto/rpc_server.py:20-110, whose shared dictionaries are unsynchronised)."""
+
     def __init__(self, ip: str = "127.0.0.1", port: int = 50051, world_size: int = 1, *,
                  relay_threshold: float = 0.1, time_slot_duration: float = 0.005,
                  fault_tolerant_time: float = 10.0, accumulated_size: float = 100 * 8 / 1024,

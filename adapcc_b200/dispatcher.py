@@ -29,6 +29,9 @@ def _local_names() -> set:
 
 
 class Dispatcher:
+    """File plane between the servers of a job: ships detect files, profile records, the logical graph and the strategy
+    XML (local hosts: copy, remote hosts: ``scp``) — /root/reference/dispatcher.py:1-54."""
+
     def __init__(self, ip_table: Sequence[str], scp: str = "scp", dry_run: bool = False):
         # ADAPCC_SHARED_FS=1: every host sees the same directory (one box, NFS, emulated multi-server
         # runs) -> plain local copies. Also the fallback when no scp binary exists.

@@ -33,6 +33,9 @@ from ..ops.layers import FusedLayerNorm, FusedLinear
 
 @dataclass
 class GPT2Config:
+    """GPT-2 small hyper-parameters (HF ``GPT2Config()`` + the five dialogue tokens) — the model of the reference's
+    flagship workload, /root/reference/models/gpt2/train_gpt2_ddp.py:157-159."""
+
     vocab_size: int = 50257 + 5          # GPT2Config() + the five PersonaChat special tokens
     n_positions: int = 1024
     n_embd: int = 768
@@ -49,6 +52,9 @@ class GPT2Config:
 
 
 class Block(nn.Module):
+    """Pre-LN transformer block; the MLP runs as two GEMMs with the activation passes in tcgen05 epilogues when
+    supported (ops/gemm.py), residual adds optionally fused into the following LayerNorm (``forward_deferred``)."""
+
     def __init__(self, cfg: GPT2Config):
         super().__init__()
         d = cfg.n_embd
@@ -185,6 +191,10 @@ class _ChunkedLMLoss(torch.autograd.Function):
 
 
 class GPT2DoubleHeads(nn.Module):
+    """GPT-2 with a tied LM head and a multiple-choice head on a chosen token (HF ``GPT2DoubleHeadsModel``):
+    ``forward`` returns the training losses (LM on labelled positions + MC over candidates); fused embedding,
+    chunked LM-head + CE, optional scored-rows-only LM head."""
+
     def __init__(self, cfg: Optional[GPT2Config] = None):
         super().__init__()
         self.cfg = cfg = cfg or GPT2Config()

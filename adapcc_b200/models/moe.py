@@ -22,6 +22,11 @@ import torch.nn.functional as F
 
 
 class MoEMLP(nn.Module):
+    """Top-k gated mixture-of-experts MLP (``num_expert`` × (d_model → d_hidden → d_model)), the layer of the
+    reference's MoE workload (``fmoe.FMoETransformerMLP``, /root/reference/models/moe/train_moe.py:37-44). Experts
+    local by default; with an ``ExpertExchange`` they are sharded over the ranks and tokens travel through the
+    native dispatch / combine kernels."""
+
     def __init__(self, num_expert: int = 10, d_model: int = 1024, d_hidden: int = 4096, top_k: int = 1,
                  world_size: int = 1, capacity_factor: float = 2.0, exchange=None):
         super().__init__()

@@ -14,6 +14,9 @@ import torch.nn.functional as F
 
 @dataclass
 class ViTConfig:
+    """The reference's ViT workload shape (``vit_pytorch.ViT(image 256, patch 32, dim 1024, depth 6, heads 16, mlp
+    2048)``, /root/reference/models/vit/train_vit.py:30-40)."""
+
     image_size: int = 224
     patch_size: int = 16
     dim: int = 768
@@ -52,6 +55,9 @@ class _Block(nn.Module):
 
 
 class ViT(nn.Module):
+    """Vision transformer classifier (patch embedding by a strided conv, pre-LN blocks with SDPA attention, class
+    token) — self-contained so the workload does not need ``vit_pytorch``."""
+
     def __init__(self, c: ViTConfig = None):
         super().__init__()
         self.cfg = c = c or ViTConfig()

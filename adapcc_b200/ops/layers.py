@@ -149,6 +149,10 @@ class _AddLayerNormFn(torch.autograd.Function):
 
 
 class FusedLayerNorm(nn.LayerNorm):
+    """``nn.LayerNorm`` whose bf16 CUDA forward / backward are single kernels (csrc/ops_norm.cu; optional residual add
+    fused in: ``forward_add``); under the flat engine the backward writes d(gamma) / d(beta) straight into the flat
+    gradient buffer (``_adapcc_grad_sink``)."""
+
     def _fusable(self, x):
         return (x.is_cuda and x.dtype == torch.bfloat16 and self.weight.dtype == torch.bfloat16
                 and x.shape[-1] in _LN_WIDTHS and len(self.normalized_shape) == 1)
@@ -217,6 +221,9 @@ def linear_backward(params, x, w, dy, needs_dx=True, db=None):
 
 
 class FusedLinear(nn.Linear):
+    """``nn.Linear`` whose backward computes dW into the engine's flat gradient view (no accumulate kernel) and the
+    bias gradient with the column-sum kernels of csrc/ops_norm.cu; the GEMMs themselves are cuBLAS."""
+
     def forward(self, x):
         if (x.is_cuda and x.dtype == torch.bfloat16 and self.bias is not None and self.weight.dtype == torch.bfloat16
                 and self.out_features % 8 == 0 and torch.is_grad_enabled()):

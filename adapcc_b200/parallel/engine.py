@@ -66,6 +66,10 @@ class _GradSink:
 
 
 class FlatDataParallel:
+    """Data-parallel training engine on flat buffers (see the module docstring): owns the parameters' and gradients'
+    storage, launches bucket collectives from gradient-ready events, runs the (sharded) optimizer, captures the
+    whole step in a CUDA graph, and checkpoints per parameter name."""
+
     def __init__(self, model: nn.Module, comm=None, *, world_size: int = 1, rank: int = 0,
                  bucket_mb: float = 32.0, lr: float = 6.25e-5, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.01, max_norm: float = 1.0, optimizer: str = "adamw",

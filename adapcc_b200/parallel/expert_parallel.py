@@ -44,6 +44,11 @@ def _s():
 
 
 class ExpertExchange:
+    """Token dispatch / combine for expert parallelism over peer memory: ``moe_push_kernel`` stores each token row
+    directly into the symmetric window of the rank that owns its expert, ``moe_pull_kernel`` reads the expert
+    outputs back (csrc/moe.cu) — the role of fastmoe's ``global_scatter / global_gather`` over grouped
+    ``ncclSend/ncclRecv`` (third-party/fastmoe/cuda/global_exchange.h:11-55), without a collective library."""
+
     def __init__(self, comm, n_expert_local: int, capacity: int, d_model: int, active: Optional[Sequence[int]] = None):
         self.comm, self.e_local, self.capacity, self.d = comm, n_expert_local, capacity, d_model
         self.world, self.rank = comm.world, comm.rank

@@ -25,6 +25,9 @@ from .trees import Strategy, Tree
 
 @dataclass
 class RelayControl:
+    """The reference's relay truth table for one rank in one tree: does it receive, contribute its own data, launch a
+    reduce kernel, send (``hasRecv / hasLocal / hasKernel / hasSend``, /root/reference/csrc/control.cu:72-101)."""
+
     has_recv: bool = False
     has_local: bool = False
     has_kernel: bool = False
@@ -54,6 +57,10 @@ def relay_control(tree: Tree, rank: int, active: Iterable[int]) -> RelayControl:
 
 @dataclass
 class TreeRole:
+    """What a rank does in one tree for one op after relay control: effective parent / children over the active subset
+    (forward: inactive ranks stay on the path; bypass: they are contracted out) and role flags — mirrored natively
+    by csrc/schedule.cpp::tree_role."""
+
     parent: int = -1
     children: List[int] = field(default_factory=list)
     flags: int = 0

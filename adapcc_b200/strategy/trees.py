@@ -25,6 +25,10 @@ class StrategyError(ValueError):
 
 @dataclass
 class Tree:
+    """One reduction / broadcast tree of a strategy: ``parent`` map over world ranks plus each node's ``ip`` (a cross-
+    server edge = different ips); child → parent edges reduce, the reverse edges broadcast
+    (/root/reference/csrc/allreduce.cu:52-104)."""
+
     root: int = -1
     nodes: List[int] = field(default_factory=list)            # DFS pre-order (document order)
     parent: Dict[int, int] = field(default_factory=dict)      # child -> parent
@@ -82,6 +86,10 @@ class Tree:
 
 @dataclass
 class Strategy:
+    """A strategy file in memory: the parallel trees (tree *t* owns slice *t* of every tensor), the ``<trees>``
+    attributes (chunk size, forced algorithm, the per-message algorithm plan) and validation / pruning to a world
+    size — the XML schema of /root/reference/strategy/*.xml."""
+
     trees: List[Tree] = field(default_factory=list)
     attrs: Dict[str, str] = field(default_factory=dict)       # optional <trees algo=".." chunk="..">
 

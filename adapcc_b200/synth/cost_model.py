@@ -17,6 +17,9 @@ GB = 1e9
 
 @dataclass
 class LinkModel:
+    """α–β description of a job's links: ``alpha(i, j)`` seconds and ``bw_gbs[i][j]`` GB/s per ordered pair, built from
+    the profile's latency / bandwidth matrices (or uniform for what-if runs)."""
+
     alpha_us: List[List[float]]     # [src][dst] one-way latency, us
     bw_gbs: List[List[float]]       # [src][dst] bandwidth, GB/s
 

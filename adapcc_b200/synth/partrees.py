@@ -77,6 +77,10 @@ def _finalise(tree: Tree) -> Tree:
 
 
 class ParTrees:
+    """The reference's parallel-trees heuristic (/root/reference/gurobi/trees.py:5-152): servers chained / paired by
+    the parity rule, GPUs inside a server arranged by ``intra_policy`` (chain | binary | star), one tree per
+    parallel transmission with rotated roots on a single NVSwitch server."""
+
     def __init__(self, intra_policy: str = "chain", rotate_single_server: bool = True):
         self.intra_policy = intra_policy
         self.rotate_single_server = rotate_single_server

@@ -36,6 +36,10 @@ def ll_time(lm: LinkModel, nbytes: float, ranks: Optional[Sequence[int]] = None)
 
 @dataclass
 class AlgoPlan:
+    """Size bands → algorithm, separately for staged tensors (``bands``) and tensors in the symmetric heap
+    (``bands_zc``); serialised into the strategy XML's attributes and consulted per message by
+    ``CudaCommu._resolve_algo``."""
+
     bands: List[Tuple[int, str]] = field(default_factory=list)       # staged: (largest wire bytes of the band, algo)
     bands_zc: List[Tuple[int, str]] = field(default_factory=list)    # tensors in the symmetric heap
     estimates_us: Dict[str, Dict[str, float]] = field(default_factory=dict)   # "<bytes>[zc]" -> algo -> us

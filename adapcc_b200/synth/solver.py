@@ -40,6 +40,11 @@ class SolverError(RuntimeError):
 
 
 class Solver:
+    """MILP synthesizer: parent choice, root choice, depth (MTZ) and ingress / egress load variables per tree, solved
+    by HiGHS (``scipy.optimize.milp``) under a time limit, best of the incumbents by the cost model; emits the
+    strategy XML and a chunk size. Same call signature as the reference's ``Solver.optimize``
+    (/root/reference/gurobi/solver.py), whose Gurobi model is never solved."""
+
     def __init__(self, time_limit_s: float = 5.0, mip_rel_gap: float = 0.02, first_limit_s: float = 1.5):
         self.time_limit_s = time_limit_s
         self.first_limit_s = first_limit_s

@@ -15,6 +15,10 @@ from .solver import Solver, SolverError
 
 
 class Synthesizer:
+    """Front end of strategy synthesis with the reference's constructor, setters and ``generate_strategy(prim) -> chunk
+    bytes`` (/root/reference/gurobi/synthesizer.py:5-62); policies: ``par-trees`` (heuristic), ``milp`` / ``gurobi``
+    (HiGHS), ``auto`` (cheaper of the two under the cost model)."""
+
     def __init__(self, strategy_file, ip_table=None, parallel_degree=4, size=10 * (10 ** 6),
                  bandwidth_graph=None, latency_graph=None, policy="par-trees", intra_policy="chain"):
         self.strategy_file = strategy_file

@@ -16,6 +16,10 @@ import torch.distributed as dist
 
 
 class State:
+    """Everything a worker needs to resume (model, optimizer, epoch, step, extras) with atomic save / load and in-
+    memory snapshots that can be broadcast to restarted workers — the ``State`` object of the reference's elastic
+    ImageNet example (/root/reference/models/image-classification/main_elastic.py:188-305)."""
+
     def __init__(self, model, optimizer, epoch: int = -1, step: int = 0, extra: Optional[Dict[str, Any]] = None):
         self.model, self.optimizer, self.epoch, self.step = model, optimizer, epoch, step
         self.extra = extra or {}

@@ -19,6 +19,11 @@ from typing import Dict, Set
 
 @dataclass
 class FaultInjector:
+    """Test / benchmark helper that makes chosen ranks slow (fixed delay, jitter, heterogeneity factor) or kills them
+    at a given step, driven by ``ADAPCC_STRAGGLERS / ADAPCC_STRAGGLE_MS / ADAPCC_JITTER / ADAPCC_STRAGGLE_FROM /
+    ADAPCC_KILL / ADAPCC_HETER_ALPHA`` — how the straggler and fault scenarios of the reference's evaluation are
+    reproduced on one box."""
+
     rank: int
     stragglers: Set[int] = field(default_factory=set)
     straggle_ms: float = 0.0

@@ -11,6 +11,9 @@ from typing import List, Optional
 
 
 class AverageMeter:
+    """Running value / average of a metric, printed as ``name val (avg)`` (the meters of the reference's ImageNet
+    scripts, /root/reference/models/image-classification/main_elastic.py:515-554)."""
+
     def __init__(self, name: str, fmt: str = ":f"):
         self.name, self.fmt = name, fmt
         self.reset()
@@ -30,6 +33,9 @@ class AverageMeter:
 
 
 class ProgressMeter:
+    """One progress line per call: ``prefix[batch/total]`` followed by the meters, tab separated (same layout as the
+    reference's trainers, so its log processors keep working)."""
+
     def __init__(self, num_batches: int, meters: List[AverageMeter], prefix: str = ""):
         n = len(str(num_batches))
         self.fmt = "[{:" + str(n) + "d}/" + ("{:" + str(n) + "d}").format(num_batches) + "]"
