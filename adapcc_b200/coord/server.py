@@ -37,6 +37,7 @@ class _Step:
     first_arrival: float = 0.0
     decided_at: float = 0.0
     served_controllers: int = 0
+    fault: bool = False                                  # a heartbeat deadline was missed in THIS step
 
 
 class Coordinator:
@@ -147,9 +148,14 @@ class Coordinator:
                     # fault: the ranks that did not report are dead from now on — later steps expect only the
                     # survivors (the reference re-runs the 10 s timeout every step, /root/reference/proto/rpc_server.py:48-59)
                     self.dead |= {r for r in range(self.world_size) if r not in st.heartbeats}
+                    st.fault = True
                     self._cv.notify_all()
-                    return list(st.heartbeats), 0           # report the survivors
+                    break
                 self._cv.wait(timeout=min(left, 0.05))
+            if st.fault:
+                # EVERY survivor of this step gets status 0 + the survivor list, not only the one whose deadline expired
+                # first (the others leave the loop because the dead no longer count)
+                return [h for h in st.heartbeats if h not in self.dead], 0
             deadline = time.time() + self.fault_tolerant_time + self.relay_threshold
             while not st.decided:
                 left = deadline - time.time()

@@ -135,7 +135,8 @@ def test_dead_rank_is_not_waited_for_again():
     ts = [threading.Thread(target=survivor, args=(r, 5)) for r in (0, 1)]       # rank 2 never reports
     [t.start() for t in ts]
     [t.join() for t in ts]
-    assert out[(0, 5, "ctl")][1] == 0 and sorted(out[(0, 5, "ctl")][0]) == [0, 1]
+    for r in (0, 1):      # BOTH survivors learn about the fault in the step it happened (not only the first to time out)
+        assert out[(r, 5, "ctl")][1] == 0 and sorted(out[(r, 5, "ctl")][0]) == [0, 1], out
     assert c.dead == {2} and time.time() - t0 >= 0.35
     t1 = time.time()
     ts = [threading.Thread(target=survivor, args=(r, 6)) for r in (0, 1)]
