@@ -266,3 +266,32 @@ def test_plan_encoding_and_pick_properties():
         assert pos == end
 
     shards_tile()
+
+
+def test_cost_model_report_reproduces_from_the_committed_sweeps(tmp_path):
+    """tools/cost_model_report.py on profiles/raw/sweep_{8,2}xB200_r2.json: at every measured size the plan's pick is the
+    fastest measured variant or within 3 % of it (staged and heap tensors, 8 GPUs where the model was fitted and 2 GPUs
+    as a hold-out)."""
+    import importlib.util
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "profiles", "raw", "sweep_8xB200_r2.json")):
+        pytest.skip("measurement files not present")
+    spec = importlib.util.spec_from_file_location("cost_model_report", os.path.join(root, "tools", "cost_model_report.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rows = 0
+    for world, trees in ((8, 3), (2, 2)):
+        for line in mod.section(world, trees):
+            if not re.match(r"\| \d+ \|", line):
+                continue
+            cells = [c.strip() for c in line.strip("|").split("|")]
+            for verdict in cells[-2:]:
+                m = re.search(r"\((=|[\d.]+x|not measured)\)$", verdict)
+                assert m, verdict
+                if m.group(1) not in ("=", "not measured"):
+                    assert float(m.group(1)[:-1]) <= 1.03, (world, cells[0], verdict)
+            rows += 1
+    assert rows >= 18
